@@ -1,0 +1,80 @@
+"""ctypes binding of libfabric_b200.so (the C ABI in include/fabric_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no fallback: if the
+library is missing, or the device is not sm_100, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfabric_b200.so")
+
+FB_OK = 0
+
+
+class FabricB200Error(RuntimeError):
+    pass
+
+
+class ConvTuning(C.Structure):
+    _fields_ = [("n_tile", C.c_int), ("halo", C.c_int), ("a_stages", C.c_int), ("b_stages", C.c_int),
+                ("b_resident", C.c_int), ("grid", C.c_int)]
+
+
+class Conv3x3Desc(C.Structure):
+    _fields_ = [
+        ("G", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("Cin", C.c_int), ("Cout", C.c_int), ("relu", C.c_int), ("store_main", C.c_int),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("y", C.c_void_p),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("pool_out", C.c_void_p), ("stats_ws", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
+        ("tune", ConvTuning),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/fabric_b200.h
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+SIGNATURES = {
+    "fabric_b200_version": (_i, []),
+    "fabric_b200_last_error": (C.c_char_p, []),
+    "fabric_b200_sm_count": (_i, []),
+    "fabric_b200_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_pack_conv3x3_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_conv3x3": (_i, [C.POINTER(Conv3x3Desc), _vp]),
+    "fabric_b200_conv3x3_grid": (_i, [C.POINTER(Conv3x3Desc)]),
+    "fabric_b200_conv3x3_stats_ws_floats": (C.c_int64, [C.POINTER(Conv3x3Desc)]),
+    "fabric_b200_bn_fold_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
+    "fabric_b200_build_up_input": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_outconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare all prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FabricB200Error(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). fabric_b200 has no CPU or eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc < 0:
+        msg = load().fabric_b200_last_error().decode("utf-8", "replace")
+        raise FabricB200Error(f"{what or 'fabric_b200'} failed ({rc}): {msg}")
+    return rc

@@ -1,0 +1,69 @@
+"""Host-side mirror of the reference's ``models/bidate_model.py`` (BiDateNet): same constructor, attribute
+names and ``state_dict`` keys; ``forward(x_d1, x_d2)`` takes NCHW fp32 [B,13,H,W] pairs and returns NCHW fp32
+logits [B,2,H,W] exactly like reference models/bidate_model.py:22-40, but runs as ~25 sm_100a kernel launches:
+
+* both dates go through the weight-shared encoder as ONE launch per conv (date group dim G=2; in training
+  mode the BatchNorm moments are still kept per date, as in the reference which calls the encoder twice);
+* MaxPool2d is fused into the producing conv's epilogue, relu(d2*d1) + bilinear upsample + pad + concat into one
+  decoder-input kernel, outconv into the last conv's epilogue.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .unet_parts import down, outconv, up, inconv
+
+
+class BiDateNet(nn.Module):
+    def __init__(self, n_channels, n_classes):
+        super(BiDateNet, self).__init__()
+        if n_channels > 16:
+            raise NotImplementedError("fabric_b200 BiDateNet supports up to 16 input bands (the reference uses 13)")
+        self.inc = inconv(n_channels, 64)
+        self.down1 = down(64, 128)
+        self.down2 = down(128, 256)
+        self.down3 = down(256, 512)
+        self.down4 = down(512, 512)
+
+        self.up1 = up(1024, 256)
+        self.up2 = up(512, 128)
+        self.up3 = up(256, 64)
+        self.up4 = up(128, 64)
+        self.outc = outconv(64, n_classes)
+        self.fuse_head = True
+
+    def pack_pair(self, x_d1, x_d2):
+        """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16]."""
+        b, c, h, w = x_d1.shape
+        x5 = torch.empty((2, b, h, w, ops.cpad(c)), dtype=torch.bfloat16, device=x_d1.device)
+        ops.pack_input(x_d1.contiguous(), out=x5[0])
+        ops.pack_input(x_d2.contiguous(), out=x5[1])
+        return x5
+
+    def forward_packed(self, x5):
+        """Eval-mode forward on an already packed pair tensor; returns NCHW fp32 logits."""
+        e1 = self.inc.run5(x5, pool=True)                       # models/bidate_model.py:23,29
+        e2 = self.down1.run5(e1["pool"], pool=True)             # :24,30
+        e3 = self.down2.run5(e2["pool"], pool=True)             # :25,31
+        e4 = self.down3.run5(e3["pool"], pool=True)             # :26,32
+        e5 = self.down4.run5(e4["pool"])                        # :27,33
+        x = self.up1.run5(e5["y"], e4["y"])["y"]                # :35
+        x = self.up2.run5(x, e3["y"])["y"]                      # :36
+        x = self.up3.run5(x, e2["y"])["y"]                      # :37
+        if self.fuse_head:
+            return self.up4.run5(x, e1["y"], head=self.outc.head(), keep_main=False)["logits"]   # :38-39
+        x = self.up4.run5(x, e1["y"])["y"]                      # :38
+        return self.outc.run5(x)                                # :39
+
+    def forward(self, x_d1, x_d2):
+        if x_d1.shape != x_d2.shape:
+            raise ValueError("x_d1 and x_d2 must have the same shape")
+        if not x_d1.is_cuda:
+            raise RuntimeError("fabric_b200.BiDateNet runs on sm_100 CUDA devices only (no CPU fallback); "
+                               "call .cuda() on the model and inputs")
+        if self.training:
+            from .autograd import bidatenet_train_forward
+            return bidatenet_train_forward(self, x_d1, x_d2)
+        return self.forward_packed(self.pack_pair(x_d1, x_d2))

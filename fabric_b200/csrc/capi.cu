@@ -1,0 +1,518 @@
+// C ABI of fabric_b200 (see include/fabric_b200.h): host-side launch logic + the small bandwidth-bound kernels.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/fabric_b200.h"
+#include "conv3x3_umma.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define FB_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(FB_ERR_LAUNCH, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceInfo {
+  int ok = 0;  // 1 = sm_100, -1 = other
+  int sms = 0;
+  int smem_optin = 0;
+};
+DeviceInfo g_dev[64];
+std::mutex g_mu;
+
+int device_info(DeviceInfo* out) {
+  int dev = 0;
+  FB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(FB_ERR_ARG, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev[dev].ok == 0) {
+    int major = 0, minor = 0;
+    FB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    FB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    FB_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    FB_CUDA(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_dev[dev].ok = (major == 10 && minor == 0) ? 1 : -1;
+  }
+  *out = g_dev[dev];
+  if (out->ok != 1) return fail(FB_ERR_ARCH, "fabric_b200 kernels are built for sm_100a only; device %d is not", dev);
+  return FB_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode(EncodeTiledFn* fn) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_encode) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !p || q != cudaDriverEntryPointSuccess)
+      return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = g_encode;
+  return FB_OK;
+}
+
+// bf16 NHWC5 tensor (C, W, H, B, G) with box (bc, bw, bh, bb, 1)
+int make_tmap_act(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int G, int bc, int bw, int bh, int bb,
+                  CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc;
+  int rc = get_encode(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)G};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                           (cuuint64_t)B * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d G=%d box %d,%d,%d,%d) -> %d", C, W, H, B, G,
+                bc, bw, bh, bb, (int)r);
+  return FB_OK;
+}
+
+// bf16 2-D row-major [rows][cols] with box (bcols, brows)
+int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int brows, int bcols, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc;
+  int rc = get_encode(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bcols, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled(2d %lld x %lld box %d x %d) -> %d", (long long)rows,
+                (long long)cols, brows, bcols, (int)r);
+  return FB_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------ conv planning
+struct ConvPlan {
+  fb::Conv3x3Params p;
+  int n_tile, ck, halo, grid, smem;
+};
+
+int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
+  if (!d) return fail(FB_ERR_ARG, "null descriptor");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (d->G < 1 || d->G > 2 || d->B < 1 || d->H < 1 || d->W < 1) return fail(FB_ERR_SHAPE, "bad G/B/H/W");
+  if (!(d->Cin == 16 || (d->Cin > 0 && d->Cin % 64 == 0))) return fail(FB_ERR_SHAPE, "Cin %d must be 16 or k*64", d->Cin);
+  if (d->Cout <= 0 || d->Cout % 64) return fail(FB_ERR_SHAPE, "Cout %d must be a multiple of 64", d->Cout);
+  const int ck = d->Cin == 16 ? 16 : 64;
+  int n_tile = d->tune.n_tile;
+  if (n_tile == 0) n_tile = d->Cout == 64 ? 64 : 128;
+  if (!(n_tile == 64 || n_tile == 128 || n_tile == 256) || d->Cout % n_tile)
+    return fail(FB_ERR_SHAPE, "n_tile %d does not divide Cout %d", n_tile, d->Cout);
+  if (ck == 16 && n_tile != 64) return fail(FB_ERR_SHAPE, "Cin=16 path is built for n_tile 64 only");
+  if (d->head_out && (d->Cout != 64 || n_tile != 64 || !d->head_w || !d->head_b))
+    return fail(FB_ERR_SHAPE, "fused head needs Cout == 64 and head weights");
+  if (!d->store_main && !d->head_out) return fail(FB_ERR_ARG, "nothing to write");
+
+  fb::Conv3x3Params& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.G = d->G, p.B = d->B, p.H = d->H, p.W = d->W, p.Cin = d->Cin, p.Cout = d->Cout;
+  if (d->H > 8) p.bh = 16;
+  else if (d->H > 4) p.bh = 8;
+  else if (d->H > 2) p.bh = 4;
+  else p.bh = 2;
+  p.bn = 16 / p.bh;
+  p.tiles_x = (d->W + 7) / 8;
+  p.tiles_y = (d->H + p.bh - 1) / p.bh;
+  p.tiles_b = (d->B + p.bn - 1) / p.bn;
+  p.num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_b * d->G;
+  p.num_n_tiles = d->Cout / n_tile;
+  p.kchunks = d->Cin / ck;
+  int halo = d->tune.halo;
+  const bool halo_ok = (ck == 64 && p.bh == 16);
+  if (halo < 0) halo = halo_ok ? 1 : 0;
+  if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs Cin %% 64 == 0 and H > 8");
+
+  const long long total = (long long)p.num_m_tiles * p.num_n_tiles;
+  int grid = d->tune.grid > 0 ? d->tune.grid : di.sms;
+  if (grid > total) grid = (int)total;
+  else grid = (grid / p.num_n_tiles) * p.num_n_tiles;  // each CTA keeps one N tile for its whole life
+  if (grid < 1) grid = (int)(total < p.num_n_tiles ? total : p.num_n_tiles);
+  const bool n_const = (grid % p.num_n_tiles == 0) || grid == total;
+  if (d->stats_ws && grid % p.num_n_tiles != 0 && grid != total)
+    return fail(FB_ERR_SHAPE, "stats need a grid that is a multiple of the N tiles");
+
+  const int a_bytes = fb::conv_a_stage_bytes(ck, halo);
+  const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck);
+  const int fixed = 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile) + 1024;
+  const int avail = di.smem_optin - fixed;
+  const int kblocks = 9 * p.kchunks;
+  int b_res = d->tune.b_resident;
+  const bool res_fits = n_const && (grid % p.num_n_tiles == 0 || p.num_n_tiles == 1 || grid == total) &&
+                        (long long)kblocks * b_bytes + 2 * a_bytes <= avail && kblocks <= 18;
+  if (b_res < 0) b_res = (res_fits && grid < total) ? 1 : 0;
+  if (b_res && !res_fits) return fail(FB_ERR_SHAPE, "resident weights do not fit (%d k-blocks of %d B)", kblocks, b_bytes);
+  // a CTA whose tiles alternate N tiles cannot keep weights resident; with grid == total each CTA has one tile
+  int a_st = d->tune.a_stages, b_st = d->tune.b_stages;
+  if (b_res) {
+    b_st = kblocks;
+    if (a_st <= 0) a_st = (avail - b_st * b_bytes) / a_bytes;
+    if (a_st > 4) a_st = 4;
+  } else if (halo) {
+    if (a_st <= 0) a_st = 2;
+    if (b_st <= 0) b_st = (avail - a_st * a_bytes) / b_bytes;
+    if (b_st > 8) b_st = 8;
+  } else {
+    int s = avail / (a_bytes + b_bytes);
+    if (s > 8) s = 8;
+    if (a_st <= 0) a_st = s;
+    if (b_st <= 0) b_st = s;
+  }
+  if (a_st < 1 || b_st < 1 || a_st > 8 || b_st > 18) return fail(FB_ERR_SHAPE, "bad stage counts %d/%d", a_st, b_st);
+  const long long smem = (long long)a_st * a_bytes + (long long)b_st * b_bytes + fixed;
+  if (smem > di.smem_optin) return fail(FB_ERR_SHAPE, "shared memory %lld > %d", smem, di.smem_optin);
+  p.a_stages = a_st, p.b_stages = b_st, p.b_resident = b_res;
+  p.relu = d->relu, p.store_main = d->store_main;
+  p.scale = d->scale, p.shift = d->shift;
+  p.pool_out = reinterpret_cast<__nv_bfloat16*>(d->pool_out);
+  p.stats_out = d->stats_ws;
+  p.head_w = d->head_w, p.head_b = d->head_b, p.head_out = d->head_out;
+  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem;
+  return FB_OK;
+}
+
+template <int N_TILE, int CK, bool HALO>
+int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY, cudaStream_t st) {
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO>;
+  FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+  k<<<pl.grid, fb::kConvThreads, pl.smem, st>>>(tA, tB, tY, pl.p);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+
+// NCHW fp32 -> NHWC bf16 (channel padded).  One block = one image row segment of 64 pixels.
+__global__ void pack_nchw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int Cpad, int H,
+                                 int W) {
+  extern __shared__ float tile[];  // [Cpad][65]
+  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 64;
+  const int nx = min(64, W - x0);
+  for (int i = threadIdx.x; i < Cpad * 64; i += blockDim.x) {
+    const int c = i / 64, x = i % 64;
+    float v = 0.f;
+    if (c < C && x < nx) v = src[(((size_t)b * C + c) * H + y) * W + x0 + x];
+    tile[c * 65 + x] = v;
+  }
+  __syncthreads();
+  __nv_bfloat16* out = dst + (((size_t)b * H + y) * W + x0) * Cpad;
+  for (int i = threadIdx.x; i < nx * Cpad / 2; i += blockDim.x) {
+    const int x = (2 * i) / Cpad, c = (2 * i) % Cpad;
+    reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(tile[c * 65 + x], tile[(c + 1) * 65 + x]);
+  }
+}
+
+// NHWC bf16 -> NCHW fp32.  One block = 32 pixels of one row x all channels (smem transpose).
+__global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int H, int W) {
+  extern __shared__ float tile[];  // [32][C+1]
+  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  const int nx = min(32, W - x0);
+  const __nv_bfloat16* in = src + (((size_t)b * H + y) * W + x0) * C;
+  for (int i = threadIdx.x; i < nx * C; i += blockDim.x) tile[(i / C) * (C + 1) + (i % C)] = __bfloat162float(in[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i / 32, x = i % 32;
+    if (x < nx) dst[(((size_t)b * C + c) * H + y) * W + x0 + x] = tile[x * (C + 1) + c];
+  }
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
+                                   int CinPad, int mode) {
+  const size_t n = mode == 0 ? (size_t)Cout * 9 * CinPad : (size_t)Cin * 9 * Cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (mode == 0) {
+      const int ci = i % CinPad, tap = (i / CinPad) % 9, co = i / ((size_t)CinPad * 9);
+      if (ci < Cin) v = w[((size_t)co * Cin + ci) * 9 + tap];
+    } else {
+      const int co = i % Cout, tap = (i / Cout) % 9, ci = i / ((size_t)Cout * 9);
+      v = w[((size_t)co * Cin + ci) * 9 + (8 - tap)];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    const float* bias, float eps, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = s;
+  shift[c] = ((bias ? bias[c] : 0.f) - rm[c]) * s + beta[c];
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = fb::bf16_lo(v.x), f[1] = fb::bf16_hi(v.x), f[2] = fb::bf16_lo(v.y), f[3] = fb::bf16_hi(v.y);
+  f[4] = fb::bf16_lo(v.z), f[5] = fb::bf16_hi(v.z), f[6] = fb::bf16_lo(v.w), f[7] = fb::bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(fb::pack_bf16x2(f[0], f[1]), fb::pack_bf16x2(f[2], f[3]), fb::pack_bf16x2(f[4], f[5]),
+                    fb::pack_bf16x2(f[6], f[7]));
+}
+
+// decoder input: [skip_d1 * skip_d2 | bilinear x2 (align_corners) of low, zero padded]; one thread = 8 channels
+__global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ low, uint4* __restrict__ out,
+                                      int B, int H, int W, int Cs, int h, int w, int Cl, int low_groups) {
+  const int Ct8 = (Cs + Cl) / 8, Cs8 = Cs / 8, Cl8 = Cl / 8;
+  const size_t total = (size_t)B * H * W * Ct8;
+  const size_t skip_g = (size_t)B * H * W * Cs8;  // one date group of skip, in uint4
+  const size_t low_g = (size_t)B * h * w * Cl8;
+  const int padT = (H - 2 * h) / 2, padL = (W - 2 * w) / 2;
+  const float sy = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+  const float sx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = i % Ct8;
+    size_t pix = i / Ct8;
+    const int x = pix % W;
+    pix /= W;
+    const int y = pix % H;
+    const int b = pix / H;
+    float r[8];
+    if (c8 < Cs8) {
+      const size_t o = (((size_t)b * H + y) * W + x) * Cs8 + c8;
+      float a[8], c[8];
+      unpack8(skip[o], a);
+      unpack8(skip[o + skip_g], c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(a[j] * c[j], 0.f);
+    } else {
+      const int cl = c8 - Cs8;
+      const int uy = y - padT, ux = x - padL;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+      if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
+        const float fy = sy * uy, fx = sx * ux;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        const float wgt[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+        const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const size_t o = (((size_t)b * h + ys[t]) * w + xs[t]) * Cl8 + cl;
+          float a[8];
+          unpack8(low[o], a);
+          if (low_groups == 2) {
+            float c[8];
+            unpack8(low[o + low_g], c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * c[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(wgt[t], a[j], r[j]);
+        }
+      }
+    }
+    out[i] = pack8(r);
+  }
+}
+
+// 1x1 head: one warp = 32 consecutive pixels, each lane one pixel; weights in smem
+__global__ void outconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ logits, int B, int H, int W, int C) {
+  extern __shared__ float sw[];  // [2][C] + [2]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 2) sw[2 * C + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t plane = (size_t)H * W, total = (size_t)B * plane;
+  const int C8 = C / 8;
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    float a0 = sw[2 * C], a1 = sw[2 * C + 1];
+    const uint4* row = x + pix * C8;
+    for (int c8 = 0; c8 < C8; ++c8) {
+      float f[8];
+      unpack8(row[c8], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0 = fmaf(f[j], sw[c8 * 8 + j], a0);
+        a1 = fmaf(f[j], sw[C + c8 * 8 + j], a1);
+      }
+    }
+    const size_t b = pix / plane, o = pix % plane;
+    logits[(b * 2 + 0) * plane + o] = a0;
+    logits[(b * 2 + 1) * plane + o] = a1;
+  }
+}
+
+int ew_grid(size_t n, int block, int sms) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = (size_t)sms * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+// ====================================================================================================== exports
+extern "C" {
+
+int fabric_b200_version(void) { return 100; }
+const char* fabric_b200_last_error(void) { return g_err; }
+
+int fabric_b200_sm_count(void) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  return rc ? rc : di.sms;
+}
+
+int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int Cpad, int H, int W, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!src || !dst) return fail(FB_ERR_ARG, "null pointer");
+  if (C < 1 || Cpad < C || Cpad % 8 || B < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return fail(FB_ERR_SHAPE, "bad shape");
+  if (!aligned16(dst)) return fail(FB_ERR_ALIGN, "dst must be 16-byte aligned");
+  dim3 grid((W + 63) / 64, H, B);
+  pack_nchw_kernel<<<grid, 256, Cpad * 65 * sizeof(float), (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), C, Cpad, H, W);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!src || !dst) return fail(FB_ERR_ARG, "null pointer");
+  if (C < 1 || C > 1024 || B < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return fail(FB_ERR_SHAPE, "bad shape");
+  const size_t smem = 32 * (size_t)(C + 1) * sizeof(float);
+  FB_CUDA(cudaFuncSetAttribute(unpack_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((W + 31) / 32, H, B);
+  unpack_nhwc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, C, H, W);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_pack_conv3x3_weight(const float* w, void* dst, int Cout, int Cin, int CinPad, int mode, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!w || !dst) return fail(FB_ERR_ARG, "null pointer");
+  if (mode != 0 && mode != 1) return fail(FB_ERR_ARG, "mode must be 0 or 1");
+  if (Cout < 1 || Cin < 1 || CinPad < Cin || (mode == 1 && CinPad != Cin)) return fail(FB_ERR_SHAPE, "bad shape");
+  const size_t n = mode == 0 ? (size_t)Cout * 9 * CinPad : (size_t)Cin * 9 * Cout;
+  pack_weight_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(dst), Cout, Cin, CinPad, mode);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_conv3x3_grid(const fb_conv3x3_desc* d) {
+  ConvPlan pl;
+  int rc = plan_conv(d, &pl);
+  return rc ? rc : pl.grid;
+}
+
+int64_t fabric_b200_conv3x3_stats_ws_floats(const fb_conv3x3_desc* d) {
+  ConvPlan pl;
+  int rc = plan_conv(d, &pl);
+  return rc ? rc : (int64_t)pl.grid * 2 * pl.n_tile * 2;
+}
+
+int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
+  ConvPlan pl;
+  int rc = plan_conv(d, &pl);
+  if (rc) return rc;
+  if (!d->x || !d->w || (d->store_main && !d->y)) return fail(FB_ERR_ARG, "null tensor pointer");
+  if (!aligned16(d->x) || !aligned16(d->w) || !aligned16(d->y) || !aligned16(d->pool_out))
+    return fail(FB_ERR_ALIGN, "tensor pointers must be 16-byte aligned");
+  const fb::Conv3x3Params& p = pl.p;
+  const CUtensorMapSwizzle sw_a = pl.ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap tA, tB, tY;
+  if (pl.halo) rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, 64, fb::kHaloW, fb::kHaloH, 1, sw_a);
+  else rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, pl.ck, 8, p.bh, p.bn, sw_a);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tB, d->w, p.Cout, 9LL * p.Cin, pl.n_tile, pl.ck, sw_a);
+  if (rc) return rc;
+  // y may be absent (head-only): the map is still needed as a kernel argument, point it at x's storage
+  if (d->store_main) rc = make_tmap_act(&tY, d->y, p.Cout, p.W, p.H, p.B, p.G, 64, 8, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  else tY = tA;
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+#define FB_DISPATCH(NT, CK, HL) \
+  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL) return launch_conv<NT, CK, HL>(pl, tA, tB, tY, st);
+  FB_DISPATCH(64, 16, false)
+  FB_DISPATCH(64, 64, false)
+  FB_DISPATCH(64, 64, true)
+  FB_DISPATCH(128, 64, false)
+  FB_DISPATCH(128, 64, true)
+  FB_DISPATCH(256, 64, false)
+  FB_DISPATCH(256, 64, true)
+#undef FB_DISPATCH
+  return fail(FB_ERR_SHAPE, "no kernel for n_tile %d ck %d halo %d", pl.n_tile, pl.ck, pl.halo);
+}
+
+int fabric_b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                             const float* conv_bias, float eps, float* scale, float* shift, int C, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift) return fail(FB_ERR_ARG, "null pointer");
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, conv_bias,
+                                                                         eps, scale, shift, C);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int B, int H, int W, int Cs, int h, int w,
+                               int Cl, int low_groups, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!skip || !low || !out) return fail(FB_ERR_ARG, "null pointer");
+  if (Cs % 8 || Cl % 8 || 2 * h > H || 2 * w > W || (low_groups != 1 && low_groups != 2)) return fail(FB_ERR_SHAPE, "bad shape");
+  if (!aligned16(skip) || !aligned16(low) || !aligned16(out)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
+  const size_t n = (size_t)B * H * W * (Cs + Cl) / 8;
+  build_up_input_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(skip), reinterpret_cast<const uint4*>(low), reinterpret_cast<uint4*>(out), B, H, W, Cs,
+      h, w, Cl, low_groups);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_outconv(const void* x, const float* w, const float* b, float* logits, int B, int H, int W, int C, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!x || !w || !b || !logits) return fail(FB_ERR_ARG, "null pointer");
+  if (C % 8 || C > 512) return fail(FB_ERR_SHAPE, "bad C");
+  const size_t n = (size_t)B * H * W;
+  outconv_kernel<<<ew_grid(n, 128, di.sms), 128, (2 * C + 2) * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), w, b, logits, B, H, W, C);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,430 @@
+// 3x3 / pad 1 / stride 1 convolution as an im2col-free implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces nn.Conv2d(in, out, 3, padding=1) (+ the BatchNorm/ReLU/MaxPool/1x1-head that follow it) at
+// reference models/unet_parts.py:13,16 (and :14-15,17-18,40,86 through the epilogue options).
+//
+//   D[m, n] = sum_{tap, c} X[pixel(m) + tap, c] * Wt[n, tap, c]         m: 128 output pixels, n: N_TILE out channels
+//
+// Data layout: activations NHWC bf16 viewed as a 5-D tensor (C, W, H, B, G) (G = date groups), weights
+// [Cout][9][Cin] bf16 (K-major), output NHWC bf16.  One CTA = one 128-pixel x N_TILE output tile, persistent
+// over tiles; 6 warps: TMA producer, MMA issuer (one elected thread, tcgen05.mma, fp32 accumulators in TMEM,
+// double buffered so the epilogue of tile i overlaps the main loop of tile i+1), 4 epilogue warps.
+//
+// Two A-operand feeding modes:
+//   TAP : one TMA box (CK ch x 8 x bh x bn) per filter tap and 64-channel chunk; zero padding = TMA OOB fill.
+//   HALO: one TMA box (64 ch x 10 x 18) per chunk = the tile plus its 1-pixel halo; the nine taps are nine
+//         UMMA shared-memory descriptors into that ONE buffer (start address shifted by (r*10+s) pixels,
+//         stride-byte-offset 1280 = one halo row), so the input crosses L2->SMEM once instead of nine times.
+#pragma once
+#include "ptx.cuh"
+
+namespace fb {
+
+struct Conv3x3Params {
+  int G, B, H, W;
+  int Cin;   // padded input channels (multiple of CK)
+  int Cout;  // multiple of N_TILE
+  int bh, bn;  // tile = bn images x bh rows x 8 columns, bh * bn == 16
+  int tiles_x, tiles_y, tiles_b;
+  int num_m_tiles, num_n_tiles;
+  int kchunks;  // Cin / CK
+  int a_stages, b_stages;
+  int b_resident;  // weights for this CTA's N tile stay in smem for the whole kernel
+  int relu;
+  int store_main;
+  const float* scale;  // per out channel, nullable (=1)
+  const float* shift;  // per out channel, nullable (=0)
+  __nv_bfloat16* pool_out;  // nullable: 2x2 max-pooled copy [G,B,H/2,W/2,Cout]
+  float* stats_out;         // nullable: per-CTA BN moment partials [grid][2][N_TILE][2] (sum, sum of squares)
+  const float* head_w;      // nullable: fused 1x1 head [2][64]
+  const float* head_b;      // [2]
+  float* head_out;          // [G*B, 2, H, W] fp32 NCHW
+};
+
+constexpr int kConvThreads = 192;
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 23040
+constexpr int kHaloStage = 23552;                  // rounded up to 1024
+
+__host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) { return halo ? kHaloStage : 128 * CK * 2; }
+__host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
+__host__ __device__ constexpr int conv_misc_bytes(int N_TILE) {
+  // scale/shift + head weights, stats slabs, barriers + tmem pointer
+  return (2 * N_TILE + 136) * 4 + 4 * 2 * N_TILE * 2 * 4 + 1024;
+}
+
+// column sums over the 32 lanes of a warp: returns sum_lanes v[lane_id]  (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float keep = b4 ? v[i + 16] : v[i], send = b4 ? v[i] : v[i + 16];
+    a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float keep = b3 ? a16[i + 8] : a16[i], send = b3 ? a16[i] : a16[i + 8];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float keep = b2 ? a8[i + 4] : a8[i], send = b2 ? a8[i] : a8[i + 4];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float keep = b1 ? a4[i + 2] : a4[i], send = b1 ? a4[i] : a4[i + 2];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  float keep = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+struct TileCoord {
+  int n0, x0, y0, b0, g;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, int N_TILE) {
+  TileCoord c;
+  int nt = t % p.num_n_tiles;
+  int m = t / p.num_n_tiles;
+  c.n0 = nt * N_TILE;
+  int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  int ty = m % p.tiles_y;
+  m /= p.tiles_y;
+  int tb = m % p.tiles_b;
+  c.g = m / p.tiles_b;
+  c.x0 = tx * 8;
+  c.y0 = ty * p.bh;
+  c.b0 = tb * p.bn;
+  return c;
+}
+
+template <int N_TILE, int CK, bool HALO>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const Conv3x3Params p) {
+  static_assert(CK == 64 || CK == 16, "channel chunk is 64 (128B swizzle) or 16 (32B swizzle)");
+  static_assert(!HALO || CK == 64, "halo mode needs 128-byte pixel rows");
+  static_assert(N_TILE == 64 || N_TILE == 128 || N_TILE == 256, "N tile");
+  constexpr int A_BYTES = conv_a_stage_bytes(CK, HALO);
+  constexpr int A_TX = HALO ? kHaloBytes : 128 * CK * 2;
+  constexpr int B_BYTES = conv_b_stage_bytes(N_TILE, CK);
+  constexpr int OUT_BYTES = 128 * N_TILE * 2;
+  constexpr uint32_t LAYOUT = (CK == 64) ? kLayoutSw128 : kLayoutSw32;
+  constexpr uint32_t ROW_BYTES = CK * 2;
+  constexpr uint32_t A_SBO = HALO ? kHaloW * 128 : 8 * ROW_BYTES;
+  constexpr uint32_t B_SBO = 8 * ROW_BYTES;
+  constexpr int TMEM_COLS = 2 * N_TILE;
+  constexpr int NCHUNK = N_TILE / 32;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+
+  const uint32_t a_off = 0;
+  const uint32_t b_off = a_off + p.a_stages * A_BYTES;
+  const uint32_t out_off = b_off + p.b_stages * B_BYTES;
+  const uint32_t ss_off = out_off + OUT_BYTES;
+  const uint32_t st_off = ss_off + (2 * N_TILE + 136) * 4;
+  const uint32_t bar_off = st_off + 4 * 2 * N_TILE * 2 * 4;
+
+  float* ss = reinterpret_cast<float*>(sm + ss_off);       // [0,N) scale, [N,2N) shift, [2N,2N+128) head w, +128.. head b
+  float* stats = reinterpret_cast<float*>(sm + st_off);    // [4 warps][2 groups][N_TILE][2]
+  const uint32_t bars = base + bar_off;
+  auto full_a = [&](int s) { return bars + 8u * s; };
+  auto empty_a = [&](int s) { return bars + 8u * (p.a_stages + s); };
+  auto full_b = [&](int s) { return bars + 8u * (2 * p.a_stages + s); };
+  auto empty_b = [&](int s) { return bars + 8u * (2 * p.a_stages + p.b_stages + s); };
+  const uint32_t tf_bar = bars + 8u * (2 * p.a_stages + 2 * p.b_stages);  // tmem_full[2], tmem_empty[2]
+  auto tmem_full = [&](int s) { return tf_bar + 8u * s; };
+  auto tmem_empty = [&](int s) { return tf_bar + 16u + 8u * s; };
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 1000);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+  }
+  if (warp == 1) {
+    tmem_alloc(base + bar_off + 1000, TMEM_COLS);
+    tmem_relinquish();
+    if (lane == 0) {
+      for (int s = 0; s < p.a_stages; ++s) {
+        mbar_init(full_a(s), 1);
+        mbar_init(empty_a(s), 1);
+      }
+      for (int s = 0; s < p.b_stages; ++s) {
+        mbar_init(full_b(s), 1);
+        mbar_init(empty_b(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tmem_full(s), 1);
+        mbar_init(tmem_empty(s), 4);
+      }
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      bool first_tile = true;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, N_TILE);
+        for (int c = 0; c < p.kchunks; ++c) {
+          if (HALO) {
+            const int s = a_it % p.a_stages;
+            mbar_wait(empty_a(s), ((a_it / p.a_stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(full_a(s), A_TX);
+            tma_load_5d(base + a_off + s * A_BYTES, &tmA, full_a(s), c * CK, tc.x0 - 1, tc.y0 - 1, tc.b0, tc.g);
+            ++a_it;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!HALO) {
+              const int s = a_it % p.a_stages;
+              mbar_wait(empty_a(s), ((a_it / p.a_stages) & 1) ^ 1);
+              mbar_arrive_expect_tx(full_a(s), A_TX);
+              tma_load_5d(base + a_off + s * A_BYTES, &tmA, full_a(s), c * CK, tc.x0 + (tap % 3) - 1,
+                          tc.y0 + (tap / 3) - 1, tc.b0, tc.g);
+              ++a_it;
+            }
+            if (!p.b_resident || first_tile) {
+              int s;
+              if (p.b_resident) {
+                s = c * 9 + tap;
+              } else {
+                s = b_it % p.b_stages;
+                mbar_wait(empty_b(s), ((b_it / p.b_stages) & 1) ^ 1);
+              }
+              mbar_arrive_expect_tx(full_b(s), B_BYTES);
+              tma_load_2d(base + b_off + s * B_BYTES, &tmB, full_b(s), tap * p.Cin + c * CK, tc.n0);
+              ++b_it;
+            }
+          }
+        }
+        first_tile = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, N_TILE, 0, 0);
+      uint32_t a_it = 0, b_it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+        const int acc = tile_it & 1;
+        mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.kchunks; ++c) {
+          int sa = 0;
+          if (HALO) {
+            sa = a_it % p.a_stages;
+            mbar_wait(full_a(sa), (a_it / p.a_stages) & 1);
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!HALO) {
+              sa = a_it % p.a_stages;
+              mbar_wait(full_a(sa), (a_it / p.a_stages) & 1);
+            }
+            int sb;
+            if (p.b_resident) {
+              sb = c * 9 + tap;
+              mbar_wait(full_b(sb), 0);
+            } else {
+              sb = b_it % p.b_stages;
+              mbar_wait(full_b(sb), (b_it / p.b_stages) & 1);
+            }
+            tc_fence_after();
+            const uint32_t a_addr = base + a_off + sa * A_BYTES + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * 128 : 0);
+            const uint32_t b_addr = base + b_off + sb * B_BYTES;
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 16, A_SBO, LAYOUT), umma_desc(b_addr + k * 32, 16, B_SBO, LAYOUT),
+                        idesc, accumulate);
+              accumulate = 1;
+            }
+            if (!p.b_resident) umma_commit(empty_b(sb));
+            ++b_it;
+            if (!HALO) {
+              umma_commit(empty_a(sa));
+              ++a_it;
+            }
+          }
+          if (HALO) {
+            umma_commit(empty_a(sa));
+            ++a_it;
+          }
+        }
+        umma_commit(tmem_full(acc));
+      }
+    }
+  } else {
+    // ================================================================ epilogue (4 warps, 128 threads)
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch
+    const int m = q * 32 + lane;        // pixel row of the tile
+    const int etid = threadIdx.x - 64;  // 0..127
+    float* my_stats = stats + q * (2 * N_TILE * 2);
+    for (int i = etid; i < 4 * 2 * N_TILE * 2; i += 128) stats[i] = 0.f;
+    if (p.head_out) {
+      for (int i = etid; i < 128; i += 128) ss[2 * N_TILE + i] = p.head_w[i];
+      if (etid < 2) ss[2 * N_TILE + 128 + etid] = p.head_b[etid];
+    }
+    const int px = m & 7;
+    const int py = (m >> 3) % p.bh;
+    const int pn = (m >> 3) / p.bh;
+    int cur_n0 = -1;
+    uint32_t tile_it = 0;
+    uint8_t* out_sm = sm + out_off;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const TileCoord tc = decode_tile(p, t, N_TILE);
+      const int acc = tile_it & 1;
+      const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
+      const bool valid = gx < p.W && gy < p.H && gb < p.B;
+      if (tc.n0 != cur_n0) {
+        for (int i = etid; i < N_TILE; i += 128) {
+          ss[i] = p.scale ? p.scale[tc.n0 + i] : 1.f;
+          ss[N_TILE + i] = p.shift ? p.shift[tc.n0 + i] : 0.f;
+        }
+        cur_n0 = tc.n0;
+      }
+      mbar_wait(tmem_full(acc), (tile_it >> 1) & 1);
+      tc_fence_after();
+      if (etid == 0) tma_store_wait_read<0>();  // staging buffer free again
+      bar_sync(1, 128);
+
+      float head0 = 0.f, head1 = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < NCHUNK; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
+        tmem_ld_wait();
+        float v[32];
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(ss + cc * 32 + j);
+          const float4 sh = *reinterpret_cast<const float4*>(ss + N_TILE + cc * 32 + j);
+          v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+
+        // staging for the TMA store: sub-tile (cc/2) of 64 channels, row m, 16-byte chunk index XOR (m & 7)
+        {
+          uint8_t* row = out_sm + (cc >> 1) * 16384 + m * 128;
+          const int cbase = (cc & 1) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = (cbase + i) ^ (m & 7);
+            *reinterpret_cast<uint4*>(row + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        }
+        if (p.stats_out) {
+          // moments of the values as stored (bf16-rounded), invalid (out-of-image) pixels contribute 0
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = valid ? bf16_lo(pk[j]) : 0.f, hi = valid ? bf16_hi(pk[j]) : 0.f;
+            s1[2 * j] = lo;
+            s1[2 * j + 1] = hi;
+            s2[2 * j] = lo * lo;
+            s2[2 * j + 1] = hi * hi;
+          }
+          const float cs1 = warp_colsum32(s1, lane);
+          const float cs2 = warp_colsum32(s2, lane);
+          float* dst = my_stats + (tc.g * N_TILE + cc * 32 + lane) * 2;
+          dst[0] += cs1;
+          dst[1] += cs2;
+        }
+        if (p.pool_out) {
+          // 2x2 max over (x^1, y^1) neighbours = lanes ^1 and ^8 of the same warp
+          uint32_t pm[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t a = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+            pm[j] = bf16x2_max(a, __shfl_xor_sync(0xffffffffu, a, 8));
+          }
+          const int Hp = p.H >> 1, Wp = p.W >> 1;
+          if (!(px & 1) && !(py & 1) && (gx >> 1) < Wp && (gy >> 1) < Hp && gb < p.B) {
+            size_t off = ((((size_t)tc.g * p.B + gb) * Hp + (gy >> 1)) * Wp + (gx >> 1)) * p.Cout + tc.n0 + cc * 32;
+            uint4* dst = reinterpret_cast<uint4*>(p.pool_out + off);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2], pm[4 * i + 3]);
+          }
+        }
+        if (p.head_out) {
+          const float* hw = ss + 2 * N_TILE;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+            head0 = fmaf(lo, hw[cc * 32 + 2 * j], head0);
+            head0 = fmaf(hi, hw[cc * 32 + 2 * j + 1], head0);
+            head1 = fmaf(lo, hw[64 + cc * 32 + 2 * j], head1);
+            head1 = fmaf(hi, hw[64 + cc * 32 + 2 * j + 1], head1);
+          }
+        }
+      }
+      // accumulator drained -> MMA may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(acc));
+
+      if (p.head_out && valid) {
+        const float* hb = ss + 2 * N_TILE + 128;
+        const size_t img = (size_t)tc.g * p.B + gb;
+        const size_t plane = (size_t)p.H * p.W;
+        p.head_out[(img * 2 + 0) * plane + (size_t)gy * p.W + gx] = head0 + hb[0];
+        p.head_out[(img * 2 + 1) * plane + (size_t)gy * p.W + gx] = head1 + hb[1];
+      }
+      fence_proxy_async_smem();
+      bar_sync(1, 128);
+      if (etid == 0 && p.store_main) {
+#pragma unroll
+        for (int j = 0; j < N_TILE / 64; ++j)
+          tma_store_5d(&tmY, base + out_off + j * 16384, tc.n0 + j * 64, tc.x0, tc.y0, tc.b0, tc.g);
+        tma_store_commit();
+      }
+    }
+    if (etid == 0) tma_store_wait_all<0>();
+    if (p.stats_out) {
+      bar_sync(1, 128);
+      float* dst = p.stats_out + (size_t)blockIdx.x * (2 * N_TILE * 2);
+      for (int i = etid; i < 2 * N_TILE * 2; i += 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += stats[w * (2 * N_TILE * 2) + i];
+        dst[i] = s;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace fb

@@ -1,0 +1,182 @@
+"""Host-side mirror of the reference's ``models/unet_parts.py``: same class names, constructor signatures,
+sub-module names and ``state_dict`` keys (so ``torch.save(model)`` / published weights round-trip), but the
+arithmetic runs in the sm_100a kernels behind the C ABI (``include/fabric_b200.h``).
+
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` objects below are parameter containers only -- their ``forward`` is never
+called.  Each block has two entry points:
+
+* ``forward(x)``: the reference's calling convention, NCHW fp32 in / NCHW fp32 out (reference
+  models/unet_parts.py:21-23,31-33,44-46,64-80,88-90);
+* ``run5(...)``: the internal fast path on NHWC5 bf16 tensors used by ``BiDateNet.forward`` so that no layout
+  change happens between blocks.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class _PackCache:
+    """Packed bf16 weights and folded BN (scale, shift), rebuilt only when the source tensors change."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, tensors, build):
+        sig = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = build()
+        self._store[key] = (sig, val)
+        return val
+
+
+class double_conv(nn.Module):
+    '''(conv => BN => ReLU) * 2   -- reference models/unet_parts.py:8-23'''
+
+    def __init__(self, in_ch, out_ch):
+        super(double_conv, self).__init__()
+        if out_ch % 64:
+            raise NotImplementedError("fabric_b200 double_conv needs out_ch to be a multiple of 64")
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_ch, out_ch, 3, padding=1),
+            nn.BatchNorm2d(out_ch),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_ch, out_ch, 3, padding=1),
+            nn.BatchNorm2d(out_ch),
+            nn.ReLU(inplace=True)
+        )
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.tune1 = None   # optional fb_conv_tuning overrides (dict), used by the benchmarks
+        self.tune2 = None
+
+    # caches are not part of the module state (and must not be pickled)
+    def _cache(self) -> _PackCache:
+        c = self.__dict__.get("_fb_cache")
+        if c is None:
+            c = _PackCache()
+            self.__dict__["_fb_cache"] = c
+        return c
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s.pop("_fb_cache", None)
+        return s
+
+    def _packed(self, idx):
+        conv = self.conv[idx]
+        return self._cache().get(("w", idx), [conv.weight], lambda: ops.pack_conv_weight(conv.weight, 0))
+
+    def _folded(self, idx):
+        conv, bn = self.conv[idx], self.conv[idx + 1]
+        return self._cache().get(("bn", idx), [bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias],
+                                 lambda: ops.bn_fold_eval(bn, conv.bias))
+
+    def run5(self, x5, pool=False, head=None, keep_main=True):
+        """NHWC5 bf16 in -> dict(y=..., pool=..., logits=...).  Eval mode: BatchNorm (running statistics), the conv
+        bias and ReLU ride in the conv epilogue; ``pool`` adds the fused MaxPool2d(2) copy for the next ``down``;
+        ``head`` = (weight[2,64], bias[2]) fuses ``outconv`` into the second conv."""
+        if self.training:
+            raise NotImplementedError("training-mode forward goes through fabric_b200.autograd (double_conv_train)")
+        s1, h1 = self._folded(0)
+        s2, h2 = self._folded(3)
+        mid = ops.conv3x3(x5, self._packed(0), self.out_ch, s1, h1, relu=True, tune=self.tune1)["y"]
+        return ops.conv3x3(mid, self._packed(3), self.out_ch, s2, h2, relu=True, pool=pool, head=head,
+                           store_main=keep_main, tune=self.tune2)
+
+    def forward(self, x):
+        x5 = ops.pack_input(x, c_pad=ops.cpad(self.in_ch)).unsqueeze(0)
+        y = self.run5(x5)["y"]
+        return ops.unpack_output(y[0])
+
+
+class inconv(nn.Module):
+    '''reference models/unet_parts.py:26-33'''
+
+    def __init__(self, in_ch, out_ch):
+        super(inconv, self).__init__()
+        self.conv = double_conv(in_ch, out_ch)
+
+    def run5(self, x5, **kw):
+        return self.conv.run5(x5, **kw)
+
+    def forward(self, x):
+        x = self.conv(x)
+        return x
+
+
+class down(nn.Module):
+    '''MaxPool2d(2) => double_conv   -- reference models/unet_parts.py:36-46.
+    On the fast path the pooling is done by the PREVIOUS block's conv epilogue (``pool=True``), so ``run5``
+    takes the already pooled tensor.'''
+
+    def __init__(self, in_ch, out_ch):
+        super(down, self).__init__()
+        self.mpconv = nn.Sequential(
+            nn.MaxPool2d(2),
+            double_conv(in_ch, out_ch)
+        )
+
+    def run5(self, pooled5, **kw):
+        return self.mpconv[1].run5(pooled5, **kw)
+
+    def forward(self, x):
+        # standalone use: pool on the packed tensor with the same kernel path (pack -> pool via torch on bf16)
+        x5 = ops.pack_input(x, c_pad=ops.cpad(self.mpconv[1].in_ch))
+        b, h, w, c = x5.shape
+        x5 = x5[:, :h // 2 * 2, :w // 2 * 2].reshape(b, h // 2, 2, w // 2, 2, c).amax(dim=(2, 4)).contiguous()
+        y = self.mpconv[1].run5(x5.unsqueeze(0))["y"]
+        return ops.unpack_output(y[0])
+
+
+class up(nn.Module):
+    '''bilinear x2 => pad => cat([skip, up]) => double_conv   -- reference models/unet_parts.py:49-80'''
+
+    def __init__(self, in_ch, out_ch, bilinear=True):
+        super(up, self).__init__()
+        if not bilinear:
+            raise NotImplementedError("the reference only ever builds up(..., bilinear=True) (models/bidate_model.py:16-19)")
+        self.up = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+        self.conv = double_conv(in_ch, out_ch)
+
+    def run5(self, low5, skip5, **kw):
+        """low5: [2,B,h,w,C] (both dates; their product is taken on the fly) or [1,B,h,w,C];
+        skip5: [2,B,H,W,Cs] encoder activations of both dates (relu(d2*d1) is fused)."""
+        cat5 = ops.build_up_input(skip5, low5)
+        return self.conv.run5(cat5, **kw)
+
+    def forward(self, x1, x2):
+        # reference calling convention: x1 = low-res tensor, x2 = (already fused) skip, both NCHW fp32
+        low5 = ops.pack_input(x1).unsqueeze(0)
+        s = ops.pack_input(x2)
+        ones = torch.ones_like(s)
+        skip5 = torch.stack([s, ones])      # skip * 1, relu is a no-op only for non-negative skips
+        if bool((x2 < 0).any()):
+            raise NotImplementedError("standalone up.forward expects a non-negative (post-ReLU) skip tensor")
+        y = self.run5(low5, skip5)["y"]
+        return ops.unpack_output(y[0])
+
+
+class outconv(nn.Module):
+    '''1x1 conv head   -- reference models/unet_parts.py:83-90'''
+
+    def __init__(self, in_ch, out_ch):
+        super(outconv, self).__init__()
+        if out_ch != 2:
+            raise NotImplementedError("fabric_b200 outconv is built for n_classes == 2 (models/bidate_model.py via helpers.py:334)")
+        self.conv = nn.Conv2d(in_ch, out_ch, 1)
+
+    def head(self):
+        """(weight [2,C] fp32, bias [2]) for fusion into the preceding conv's epilogue."""
+        w = self.conv.weight.detach()
+        return w.reshape(w.shape[0], w.shape[1]).contiguous(), self.conv.bias.detach()
+
+    def run5(self, x5):
+        return ops.outconv(x5, self.conv.weight, self.conv.bias)
+
+    def forward(self, x):
+        x5 = ops.pack_input(x, c_pad=x.shape[1]).unsqueeze(0)
+        return self.run5(x5)

@@ -1,0 +1,82 @@
+"""CPU: the oracle reproduces the numbers the unmodified reference produced (tests/golden, written by
+oracle/make_golden.py in the build container where /root/reference is mounted)."""
+import torch
+
+from oracle import bidatenet_oracle as O
+
+
+def _sd(golden):
+    sd = O.make_state_dict(seed=0)
+    for k in ("inc.conv.conv.0.weight", "down4.mpconv.1.conv.3.weight", "up1.conv.conv.0.weight", "outc.conv.weight"):
+        assert torch.allclose(sd[k].double().sum(), golden["sd_sum/" + k], rtol=0, atol=1e-9), k
+        assert torch.allclose(sd[k].double().abs().sum(), golden["sd_abssum/" + k], rtol=0, atol=1e-9), k
+    return sd
+
+
+def test_state_dict_spec_matches_reference_keys():
+    spec = O.state_dict_spec()
+    assert len(spec) == 128
+    n_float = sum(int(torch.tensor(s).prod()) if len(s) else 1 for k, s, d in spec if d == torch.float32)
+    assert n_float == 13409090                      # SURVEY: params + running stats
+    n_param = sum(int(torch.tensor(s).prod()) for k, s, d in spec if d == torch.float32 and "running_" not in k)
+    assert n_param == 13401154                      # 13,401,154 parameters
+
+
+def test_eval_forward_config1(golden):
+    sd = _sd(golden)
+    out = O.bidatenet_forward(golden["c1_x1"], golden["c1_x2"], sd, training=False)
+    assert torch.allclose(out, golden["c1_logits_eval"], rtol=0, atol=1e-5)
+
+
+def test_eval_forward_patch90_pad_branch(golden):
+    sd = _sd(golden)
+    out = O.bidatenet_forward(golden["p90_x1"], golden["p90_x2"], sd, training=False)
+    assert torch.allclose(out, golden["p90_logits_eval"], rtol=0, atol=1e-5)
+
+
+def test_losses_3d_and_4d_labels(golden):
+    logits, labels = golden["c1_logits_eval"], golden["c1_labels"]
+    crit = {"dice": O.dice_loss, "jaccard": O.jaccard_loss,
+            "tversky": lambda l, t: O.tversky_loss(l, t, 0.1, 0.9), "focal": lambda l, t: O.focal_loss(l, t, 2.0)}
+    for name, fn in crit.items():
+        for nd, lab in (("3d", labels), ("4d", labels[:, None])):
+            l = logits.clone().requires_grad_(True)
+            v = fn(l, lab)
+            v.backward()
+            assert torch.allclose(v.detach(), golden[f"c1_loss_{name}_{nd}"], rtol=0, atol=1e-6), (name, nd)
+            assert torch.allclose(l.grad, golden[f"c1_dlogits_{name}_{nd}"], rtol=1e-5, atol=1e-9), (name, nd)
+    # the dims quirk: 3-D labels reduce over (batch, H) only, so the two conventions differ
+    assert abs(float(golden["c1_loss_dice_3d"]) - float(golden["c1_loss_dice_4d"])) > 1e-6
+
+
+def test_train_step_config1(golden):
+    sd = _sd(golden)
+    loss, logits, grads, new = O.train_step(golden["c1_x1"], golden["c1_x2"], golden["c1_labels"], sd,
+                                            lambda l, t: O.tversky_loss(l, t, 0.1, 0.9))
+    assert torch.allclose(logits, golden["c1_logits_train"], rtol=0, atol=5e-5)
+    assert abs(float(loss) - float(golden["c1_loss_train"])) < 1e-6
+    for k, g in grads.items():
+        ref_norm = golden["c1_gradnorm/" + k]
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            assert g.abs().max() < 1e-5          # conv bias under train-mode BN: true gradient is zero
+            continue
+        assert abs(float(g.norm()) - float(ref_norm)) <= 5e-4 * float(ref_norm) + 1e-9, k
+        assert torch.allclose(g.flatten()[:64], golden["c1_gradhead/" + k], rtol=2e-3, atol=1e-6 + 2e-4 * float(ref_norm)), k
+    for k, v in new.items():
+        assert torch.allclose(v.float(), golden["c1_newstat/" + k].float(), rtol=1e-5, atol=1e-6), k
+    # encoder BNs see two calls per step (date 1, date 2), decoder BNs one
+    assert int(new["inc.conv.conv.1.num_batches_tracked"]) == 2
+    assert int(new["up4.conv.conv.4.num_batches_tracked"]) == 1
+
+
+def test_tiler_roundtrip():
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for (h, w, p) in ((200, 150, 64), (128, 128, 64), (130, 70, 32)):
+        bands = rng.standard_normal((h, w, 13)).astype(np.float32)
+        patches, hs, ws, lc, lr, hh, ww = O.get_patches(bands, p)
+        assert patches.shape == (hs * ws + lc + lr + 1, p, p, 13)
+        assert (hs, ws, lc, lr) == (h // p, w // p, h // p, w // p)
+        # reassembling channel 0 of the patches gives back channel 0 of the scene (later writes win)
+        img = O.get_bands(patches[..., 0], hs, ws, lc, lr, hh, ww, p)
+        assert np.array_equal(img.astype(np.float32), bands[..., 0])
