@@ -1,0 +1,312 @@
+"""bench.py -- patch-pairs/s of the BiDateNet hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of 64 synthetic 13x256x256 patch pairs per GPU:
+  infer (BASELINE.json configs[1]): eval-mode forward (reference train.py:193);
+  train (configs[2]): forward + Tversky loss + backward (+ gradient all-reduce for N > 1) -- once built.
+Prints ONE JSON line (see README / DESIGN.md section "Measurement").  For N > 1 launch with torchrun; ranks
+shard pairs data-parallel (weak scaling, 64 pairs per rank).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_GFLOP_PER_PAIR = 92.577      # SURVEY.md 8d, true Cin = 13
+TRAIN_GFLOP_PER_PAIR = 275.8
+PAIRS = 64
+SIZE = 256
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median of the samples under load (upper half)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def cpu_reference_throughput(workload, budget_s=12.0, batch=2, threads=None):
+    """The oracle port (fp32 torch CPU restatement of the reference, oracle/bidatenet_oracle.py) on the host cores,
+    on a bounded sample of the same workload: `batch` pairs of 13x256x256 per iteration."""
+    import torch
+    from oracle import bidatenet_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict(seed=0)
+    x1, x2, labels = O.make_inputs(batch, SIZE, seed=1)
+    crit = lambda l, t: O.tversky_loss(l, t, 0.1, 0.9)   # noqa: E731
+
+    def one():
+        if workload == "train":
+            O.train_step(x1, x2, labels, sd, crit)
+        else:
+            with torch.no_grad():
+                O.bidatenet_forward(x1, x2, sd, training=False)
+    one()  # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=batch / med, unit="patch-pairs/s", cores=threads, kind="port",
+                sample=f"{len(times)} iterations of {batch} pairs 13x{SIZE}x{SIZE} ({workload}), median; "
+                       f"oracle/bidatenet_oracle.py fp32 torch-CPU, {threads} threads")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (here: the oracle port, because the
+    reference is Python and /root/reference does not exist on the GPU box), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2
+    import torch
+    from oracle import bidatenet_oracle as O
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict(seed=0)
+    x1, x2, labels = O.make_inputs(batch, SIZE, seed=1)
+    crit = lambda l, t: O.tversky_loss(l, t, 0.1, 0.9)   # noqa: E731
+
+    def one():
+        if args.workload == "train":
+            O.train_step(x1, x2, labels, sd, crit)
+        else:
+            with torch.no_grad():
+                O.bidatenet_forward(x1, x2, sd, training=False)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = batch * args.steps / dt
+    sample = f"{args.steps} steps of {batch} pairs 13x{SIZE}x{SIZE} ({args.workload}); oracle port, fp32 torch-CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": "patch-pairs/s (13x256x256)", "value": v, "unit": "patch-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.workload, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "patch-pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "patch-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def config_dict(workload, n):
+    return {"workload": ("BiDateNet fwd-only inference" if workload == "infer" else
+                         "BiDateNet fwd+bwd training step, Tversky(0.1,0.9) loss") +
+                        f", 13x{SIZE}x{SIZE}, batch {PAIRS} pairs per GPU",
+            "pairs_per_gpu": PAIRS, "patch": [13, SIZE, SIZE], "global_batch": PAIRS * n,
+            "parallelism": f"dp{n}" if n > 1 else "single",
+            "cache": "inputs (2 x 218 MB fp32) and activations (> 1 GB per layer) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--impl", default="fabric_b200", choices=["fabric_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fabric_b200 import BiDateNet, ops
+    from fabric_b200.inference import HostPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == args.gpus or (world == 1 and args.gpus == 1), f"launch with torchrun for --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "train":
+        raise SystemExit("train workload: backward kernels are not built yet (round 1 measures configs[1])")
+
+    torch.manual_seed(0)
+    model = BiDateNet(13, 2).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x1 = torch.randn(PAIRS, 13, SIZE, SIZE, device=dev, generator=g)
+    x2 = torch.randn(PAIRS, 13, SIZE, SIZE, device=dev, generator=g)
+
+    def step():
+        with torch.no_grad():
+            return model(x1, x2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.CONV_PROFILE = []
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - l0
+    prof, ops.CONV_PROFILE = ops.CONV_PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_step = total_ms / args.steps
+    value = PAIRS * world * args.steps / (total_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (conv3x3_umma_kernel: 18 launches per step), measured live -----------
+    peaks = load_peaks()
+    conv_ms = sum(a.elapsed_time(b) for _, a, b, _ in prof)
+    conv_flops = sum(f for _, _, _, f in prof)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    per_layer = {}
+    for tag, a, b, f in prof:
+        d = per_layer.setdefault(tag, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b); d[1] += f; d[2] += 1
+    layers = {k: {"ms": v[0] / v[2], "tflops": v[1] / (v[0] / 1e3) / 1e12, "launches_per_step": v[2] // args.steps}
+              for k, v in per_layer.items()}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "conv3x3_umma_kernel (all 18 launches of a step)",
+                "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops"],
+                "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "conv_share_of_step": conv_ms / total_ms, "traffic": traffic,
+                "algorithmic_gflop_per_step": conv_flops / args.steps / 1e9}
+
+    # ---- end to end: host (pinned) -> device -> forward -> logits back to host, through the public API ---------
+    e2e = None
+    if True:
+        hp1 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
+        hp2 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
+        hout = torch.empty(PAIRS, 2, SIZE, SIZE).pin_memory()
+        pipe = HostPipeline(model, chunk=16, n_channels=13, size=SIZE, return_logits=True)
+        for _ in range(2):
+            pipe.run(hp1, hp2, hout)
+        barrier()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            h2d, d2h = pipe.run(hp1, hp2, hout)
+        b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([max(a.elapsed_time(b) / 1e3, wall)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": PAIRS * world * args.e2e_steps / float(tt.item()), "unit": "patch-pairs/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "api": "fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, 16-pair sub-batches)"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_throughput(args.workload)
+        out = {
+            "metric": "patch-pairs/s (13x256x256)", "value": value, "unit": "patch-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": config_dict(args.workload, world),
+            "tflops_per_gpu": FWD_GFLOP_PER_PAIR * PAIRS / ms_step,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "layers": layers,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

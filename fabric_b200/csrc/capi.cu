@@ -1,117 +1,10 @@
 // C ABI of fabric_b200 (see include/fabric_b200.h): host-side launch logic + the small bandwidth-bound kernels.
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <mutex>
-
-#include "../../include/fabric_b200.h"
+#include "host_common.cuh"
 #include "conv3x3_umma.cuh"
 
+using namespace fbh;
+
 namespace {
-
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-  return code;
-}
-
-#define FB_CUDA(call)                                                                                   \
-  do {                                                                                                  \
-    cudaError_t e_ = (call);                                                                            \
-    if (e_ != cudaSuccess) return fail(FB_ERR_LAUNCH, "%s failed: %s", #call, cudaGetErrorString(e_)); \
-  } while (0)
-
-struct DeviceInfo {
-  int ok = 0;  // 1 = sm_100, -1 = other
-  int sms = 0;
-  int smem_optin = 0;
-};
-DeviceInfo g_dev[64];
-std::mutex g_mu;
-
-int device_info(DeviceInfo* out) {
-  int dev = 0;
-  FB_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(FB_ERR_ARG, "device index %d out of range", dev);
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_dev[dev].ok == 0) {
-    int major = 0, minor = 0;
-    FB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-    FB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
-    FB_CUDA(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
-    FB_CUDA(cudaDeviceGetAttribute(&g_dev[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    g_dev[dev].ok = (major == 10 && minor == 0) ? 1 : -1;
-  }
-  *out = g_dev[dev];
-  if (out->ok != 1) return fail(FB_ERR_ARCH, "fabric_b200 kernels are built for sm_100a only; device %d is not", dev);
-  return FB_OK;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-
-int get_encode(EncodeTiledFn* fn) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_encode) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-    if (e != cudaSuccess || !p || q != cudaDriverEntryPointSuccess)
-      return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-    g_encode = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  *fn = g_encode;
-  return FB_OK;
-}
-
-// bf16 NHWC5 tensor (C, W, H, B, G) with box (bc, bw, bh, bb, 1)
-int make_tmap_act(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int G, int bc, int bw, int bh, int bb,
-                  CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc;
-  int rc = get_encode(&enc);
-  if (rc) return rc;
-  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)G};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
-                           (cuuint64_t)B * H * W * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d G=%d box %d,%d,%d,%d) -> %d", C, W, H, B, G,
-                bc, bw, bh, bb, (int)r);
-  return FB_OK;
-}
-
-// bf16 2-D row-major [rows][cols] with box (bcols, brows)
-int make_tmap_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int brows, int bcols, CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc;
-  int rc = get_encode(&enc);
-  if (rc) return rc;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)bcols, (cuuint32_t)brows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(FB_ERR_LAUNCH, "cuTensorMapEncodeTiled(2d %lld x %lld box %d x %d) -> %d", (long long)rows,
-                (long long)cols, brows, bcols, (int)r);
-  return FB_OK;
-}
-
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ------------------------------------------------------------------------------------------------ conv planning
 struct ConvPlan {
@@ -129,7 +22,7 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (d->Cout <= 0 || d->Cout % 64) return fail(FB_ERR_SHAPE, "Cout %d must be a multiple of 64", d->Cout);
   const int ck = d->Cin == 16 ? 16 : 64;
   int n_tile = d->tune.n_tile;
-  if (n_tile == 0) n_tile = d->Cout == 64 ? 64 : 128;
+  if (n_tile == 0) n_tile = d->Cout == 64 ? 64 : (d->Cout % 256 == 0 ? 256 : 128);
   if (!(n_tile == 64 || n_tile == 128 || n_tile == 256) || d->Cout % n_tile)
     return fail(FB_ERR_SHAPE, "n_tile %d does not divide Cout %d", n_tile, d->Cout);
   if (ck == 16 && n_tile != 64) return fail(FB_ERR_SHAPE, "Cin=16 path is built for n_tile 64 only");
@@ -174,6 +67,7 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   const bool res_fits = n_const && (grid % p.num_n_tiles == 0 || p.num_n_tiles == 1 || grid == total) &&
                         (long long)kblocks * b_bytes + 2 * a_bytes <= avail && kblocks <= 18;
   if (b_res < 0) b_res = (res_fits && grid < total) ? 1 : 0;
+  if (ck == 16) b_res = 1;  // the 13-band stem keeps its 18 KB of weights resident and stages all nine taps at once
   if (b_res && !res_fits) return fail(FB_ERR_SHAPE, "resident weights do not fit (%d k-blocks of %d B)", kblocks, b_bytes);
   // a CTA whose tiles alternate N tiles cannot keep weights resident; with grid == total each CTA has one tile
   int a_st = d->tune.a_stages, b_st = d->tune.b_stages;
@@ -204,9 +98,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   return FB_OK;
 }
 
-template <int N_TILE, int CK, bool HALO>
+template <int N_TILE, int CK, bool HALO, bool RES>
 int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY, cudaStream_t st) {
-  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO>;
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   k<<<pl.grid, fb::kConvThreads, pl.smem, st>>>(tA, tB, tY, pl.p);
   FB_CUDA(cudaGetLastError());
@@ -367,11 +261,6 @@ __global__ void outconv_kernel(const uint4* __restrict__ x, const float* __restr
   }
 }
 
-int ew_grid(size_t n, int block, int sms) {
-  size_t g = (n + block - 1) / block;
-  const size_t cap = (size_t)sms * 16;
-  return (int)(g < cap ? (g ? g : 1) : cap);
-}
 
 }  // namespace
 
@@ -461,17 +350,22 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   else tY = tA;
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-#define FB_DISPATCH(NT, CK, HL) \
-  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL) return launch_conv<NT, CK, HL>(pl, tA, tB, tY, st);
-  FB_DISPATCH(64, 16, false)
-  FB_DISPATCH(64, 64, false)
-  FB_DISPATCH(64, 64, true)
-  FB_DISPATCH(128, 64, false)
-  FB_DISPATCH(128, 64, true)
-  FB_DISPATCH(256, 64, false)
-  FB_DISPATCH(256, 64, true)
+  const bool res = p.b_resident != 0;
+#define FB_DISPATCH(NT, CK, HL, RS) \
+  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) return launch_conv<NT, CK, HL, RS>(pl, tA, tB, tY, st);
+  FB_DISPATCH(64, 16, false, true)
+  FB_DISPATCH(64, 64, false, false)
+  FB_DISPATCH(64, 64, false, true)
+  FB_DISPATCH(64, 64, true, false)
+  FB_DISPATCH(64, 64, true, true)
+  FB_DISPATCH(128, 64, false, false)
+  FB_DISPATCH(128, 64, false, true)
+  FB_DISPATCH(128, 64, true, false)
+  FB_DISPATCH(128, 64, true, true)
+  FB_DISPATCH(256, 64, false, false)
+  FB_DISPATCH(256, 64, true, false)
 #undef FB_DISPATCH
-  return fail(FB_ERR_SHAPE, "no kernel for n_tile %d ck %d halo %d", pl.n_tile, pl.ck, pl.halo);
+  return fail(FB_ERR_SHAPE, "no kernel for n_tile %d ck %d halo %d resident %d", pl.n_tile, pl.ck, pl.halo, (int)res);
 }
 
 int fabric_b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,

@@ -46,7 +46,10 @@ constexpr int kHaloW = 10, kHaloH = 18;
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 23040
 constexpr int kHaloStage = 23552;                  // rounded up to 1024
 
-__host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) { return halo ? kHaloStage : 128 * CK * 2; }
+// one A stage: the halo tile (HALO), all nine 128px x 16ch tap boxes (Cin = 16), or one 128px x 64ch tap box
+__host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) {
+  return halo ? kHaloStage : (CK == 16 ? 9 * 128 * 16 * 2 : 128 * CK * 2);
+}
 __host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
 __host__ __device__ constexpr int conv_misc_bytes(int N_TILE) {
   // scale/shift + head weights, stats slabs, barriers + tmem pointer
@@ -101,7 +104,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, 
   return c;
 }
 
-template <int N_TILE, int CK, bool HALO>
+template <int N_TILE, int CK, bool HALO, bool RES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const Conv3x3Params p) {
@@ -176,99 +179,175 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0;
-      bool first_tile = true;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t, N_TILE);
-        for (int c = 0; c < p.kchunks; ++c) {
-          if (HALO) {
-            const int s = a_it % p.a_stages;
-            mbar_wait(empty_a(s), ((a_it / p.a_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(full_a(s), A_TX);
-            tma_load_5d(base + a_off + s * A_BYTES, &tmA, full_a(s), c * CK, tc.x0 - 1, tc.y0 - 1, tc.b0, tc.g);
-            ++a_it;
-          }
-          for (int tap = 0; tap < 9; ++tap) {
-            if (!HALO) {
-              const int s = a_it % p.a_stages;
-              mbar_wait(empty_a(s), ((a_it / p.a_stages) & 1) ^ 1);
-              mbar_arrive_expect_tx(full_a(s), A_TX);
-              tma_load_5d(base + a_off + s * A_BYTES, &tmA, full_a(s), c * CK, tc.x0 + (tap % 3) - 1,
-                          tc.y0 + (tap / 3) - 1, tc.b0, tc.g);
-              ++a_it;
-            }
-            if (!p.b_resident || first_tile) {
-              int s;
-              if (p.b_resident) {
-                s = c * 9 + tap;
-              } else {
-                s = b_it % p.b_stages;
-                mbar_wait(empty_b(s), ((b_it / p.b_stages) & 1) ^ 1);
-              }
-              mbar_arrive_expect_tx(full_b(s), B_BYTES);
-              tma_load_2d(base + b_off + s * B_BYTES, &tmB, full_b(s), tap * p.Cin + c * CK, tc.n0);
-              ++b_it;
-            }
-          }
-        }
-        first_tile = false;
+  // ring position = (stage, phase) advanced without integer division (these loops are the issue-rate critical path)
+  struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+      if (++stage == n) {
+        stage = 0;
+        phase ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, N_TILE, 0, 0);
-      uint32_t a_it = 0, b_it = 0, tile_it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-        const int acc = tile_it & 1;
-        mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        uint32_t accumulate = 0;
-        for (int c = 0; c < p.kchunks; ++c) {
-          int sa = 0;
-          if (HALO) {
-            sa = a_it % p.a_stages;
-            mbar_wait(full_a(sa), (a_it / p.a_stages) & 1);
-          }
-          for (int tap = 0; tap < 9; ++tap) {
-            if (!HALO) {
-              sa = a_it % p.a_stages;
-              mbar_wait(full_a(sa), (a_it / p.a_stages) & 1);
-            }
-            int sb;
-            if (p.b_resident) {
-              sb = c * 9 + tap;
-              mbar_wait(full_b(sb), 0);
-            } else {
-              sb = b_it % p.b_stages;
-              mbar_wait(full_b(sb), (b_it / p.b_stages) & 1);
-            }
-            tc_fence_after();
-            const uint32_t a_addr = base + a_off + sa * A_BYTES + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * 128 : 0);
-            const uint32_t b_addr = base + b_off + sb * B_BYTES;
+  };
+  constexpr int TAPS_PER_A = (HALO || CK == 16) ? 9 : 1;  // filter taps served by one A stage
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (whole warp loops, one lane issues)
+    Ring ra, rb;
+    bool first_tile = true;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t, N_TILE);
+      for (int c = 0; c < p.kchunks; ++c) {
+        for (int tap = 0; tap < 9; ++tap) {
+          if (tap % TAPS_PER_A == 0) {
+            mbar_wait(empty_a(ra.stage), ra.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t dst = base + a_off + ra.stage * A_BYTES;
+              if (HALO) {
+                mbar_arrive_expect_tx(full_a(ra.stage), A_TX);
+                tma_load_5d(dst, &tmA, full_a(ra.stage), c * CK, tc.x0 - 1, tc.y0 - 1, tc.b0, tc.g);
+              } else if (CK == 16) {
+                mbar_arrive_expect_tx(full_a(ra.stage), 9 * A_TX);
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k) {
-              umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 16, A_SBO, LAYOUT), umma_desc(b_addr + k * 32, 16, B_SBO, LAYOUT),
-                        idesc, accumulate);
-              accumulate = 1;
+                for (int tt = 0; tt < 9; ++tt)
+                  tma_load_5d(dst + tt * A_TX, &tmA, full_a(ra.stage), c * CK, tc.x0 + (tt % 3) - 1, tc.y0 + (tt / 3) - 1,
+                              tc.b0, tc.g);
+              } else {
+                mbar_arrive_expect_tx(full_a(ra.stage), A_TX);
+                tma_load_5d(dst, &tmA, full_a(ra.stage), c * CK, tc.x0 + (tap % 3) - 1, tc.y0 + (tap / 3) - 1, tc.b0, tc.g);
+              }
             }
-            if (!p.b_resident) umma_commit(empty_b(sb));
-            ++b_it;
-            if (!HALO) {
-              umma_commit(empty_a(sa));
-              ++a_it;
-            }
+            __syncwarp();
+            ra.advance(p.a_stages);
           }
-          if (HALO) {
-            umma_commit(empty_a(sa));
-            ++a_it;
+          if constexpr (!RES) {
+            mbar_wait(empty_b(rb.stage), rb.phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_b(rb.stage), B_BYTES);
+              tma_load_2d(base + b_off + rb.stage * B_BYTES, &tmB, full_b(rb.stage), tap * p.Cin + c * CK, tc.n0);
+            }
+            __syncwarp();
+            rb.advance(p.b_stages);
+          } else if (first_tile) {  // RES: the CTA's weight slab is loaded once
+            if (elect_one()) {
+              const int s = c * 9 + tap;
+              mbar_arrive_expect_tx(full_b(s), B_BYTES);
+              tma_load_2d(base + b_off + s * B_BYTES, &tmB, full_b(s), tap * p.Cin + c * CK, tc.n0);
+            }
+            __syncwarp();
           }
         }
-        umma_commit(tmem_full(acc));
+      }
+      first_tile = false;
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (whole warp loops, one lane issues)
+    // This warp's instruction stream is the critical path of the kernel (one thread feeds the tensor core), so the
+    // loop is kept lean: taps fully unrolled with constant descriptor offsets, descriptors = base + small adds.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N_TILE, 0, 0);
+    constexpr uint64_t a_hi = umma_desc(0, 16, A_SBO, LAYOUT) & 0xFFFFFFFF00000000ull;
+    constexpr uint64_t b_hi = umma_desc(0, 16, B_SBO, LAYOUT) & 0xFFFFFFFF00000000ull;
+    constexpr uint32_t lo_fixed = static_cast<uint32_t>(umma_desc(0, 16, 0, 0) & 0xFFFFFFFFu);
+    const uint32_t a_lo_base = lo_fixed + ((base + a_off) >> 4);   // smem < 256 KB: the 14-bit field cannot overflow
+    const uint32_t b_lo_base = lo_fixed + ((base + b_off) >> 4);
+    constexpr uint32_t A_STEP = A_BYTES >> 4, B_STEP = B_BYTES >> 4;
+    Ring ra, rb;
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int acc = tile_it & 1;
+      mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      uint32_t accumulate = 0;
+      for (int c = 0; c < p.kchunks; ++c) {
+        const bool last_chunk = (c == p.kchunks - 1);
+        if constexpr (TAPS_PER_A == 9) {
+          const int sa = ra.stage;
+          mbar_wait(full_a(sa), ra.phase);
+          ra.advance(p.a_stages);
+          const uint32_t a_lo = a_lo_base + sa * A_STEP;
+          if constexpr (RES) {
+            // weights resident: nothing to wait for per tap -> one straight-line run of 9 * CK/16 MMAs per chunk
+            if (tile_it == 0) {
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) mbar_wait(full_b(c * 9 + tap), 0);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_lo = b_lo_base + c * 9 * B_STEP;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t a_tap = a_lo + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * 8 : tap * (A_TX >> 4));
+#pragma unroll
+                for (int k = 0; k < CK / 16; ++k) {
+                  umma_bf16(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_lo + tap * B_STEP + 2 * k), idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(empty_a(sa));
+              if (last_chunk) umma_commit(tmem_full(acc));
+            }
+            __syncwarp();
+            accumulate = 1;
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int sb = rb.stage;
+              mbar_wait(full_b(sb), rb.phase);
+              rb.advance(p.b_stages);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_tap = a_lo + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * 8 : tap * (A_TX >> 4));
+                const uint32_t b_lo = b_lo_base + sb * B_STEP;
+#pragma unroll
+                for (int k = 0; k < CK / 16; ++k) {
+                  umma_bf16(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_lo + 2 * k), idesc, accumulate);
+                  accumulate = 1;
+                }
+                umma_commit(empty_b(sb));
+                if (tap == 8) {
+                  umma_commit(empty_a(sa));
+                  if (last_chunk) umma_commit(tmem_full(acc));
+                }
+              }
+              __syncwarp();
+              accumulate = 1;
+            }
+          }
+        } else {
+          // per-tap A boxes (TAP mode, 64-channel chunks): both operands arrive per tap
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int sa = ra.stage;
+            mbar_wait(full_a(sa), ra.phase);
+            ra.advance(p.a_stages);
+            int sb;
+            if constexpr (RES) {
+              sb = c * 9 + tap;
+              if (tile_it == 0) mbar_wait(full_b(sb), 0);
+            } else {
+              sb = rb.stage;
+              mbar_wait(full_b(sb), rb.phase);
+              rb.advance(p.b_stages);
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo_base + sa * A_STEP;
+              const uint32_t b_lo = b_lo_base + sb * B_STEP;
+#pragma unroll
+              for (int k = 0; k < CK / 16; ++k) {
+                umma_bf16(d_tmem, a_hi | (a_lo + 2 * k), b_hi | (b_lo + 2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+              if constexpr (!RES) umma_commit(empty_b(sb));
+              umma_commit(empty_a(sa));
+              if (last_chunk && tap == 8) umma_commit(tmem_full(acc));
+            }
+            __syncwarp();
+            accumulate = 1;
+          }
+        }
       }
     }
   } else {

@@ -1,0 +1,76 @@
+"""Host-buffer inference loop: the B200 version of the reference's full-scene prediction loop
+(train.py:187-201): patches live in HOST memory (numpy / pinned torch), are copied to the device in
+sub-batches, run through ``BiDateNet`` and the logits (or the argmax change mask, train.py:199) come back to the
+host.  Unlike the reference's loop (synchronous ``.to(dev)`` -> forward -> ``.cpu()`` per batch), the copies of
+sub-batch i+1 and the read-back of sub-batch i-1 overlap the compute of sub-batch i on separate CUDA streams.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class HostPipeline:
+    """Reusable pinned staging + streams for ``predict_patches``."""
+
+    def __init__(self, model, chunk: int = 16, n_channels: int = 13, size: int = 256, return_logits: bool = True):
+        self.model = model
+        self.chunk = chunk
+        self.dev = next(model.parameters()).device
+        self.copy_in = torch.cuda.Stream(self.dev)
+        self.copy_out = torch.cuda.Stream(self.dev)
+        self.return_logits = return_logits
+        self.bufs = [dict(x1=torch.empty((chunk, n_channels, size, size), device=self.dev),
+                          x2=torch.empty((chunk, n_channels, size, size), device=self.dev),
+                          ready=torch.cuda.Event(), done=torch.cuda.Event(), out=None, copied=torch.cuda.Event())
+                     for _ in range(2)]
+
+    @torch.no_grad()
+    def run(self, x1_host: torch.Tensor, x2_host: torch.Tensor, out_host: torch.Tensor):
+        """x*_host: [N,C,S,S] fp32 (pinned for async copies); out_host: [N,2,S,S] fp32 or [N,S,S] uint8 (mask)."""
+        n = x1_host.shape[0]
+        main = torch.cuda.current_stream(self.dev)
+        h2d = d2h = 0
+        for i, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(lo + self.chunk, n)
+            b = self.bufs[i & 1]
+            k = hi - lo
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(b["done"])          # compute that last used this buffer has finished
+                b["x1"][:k].copy_(x1_host[lo:hi], non_blocking=True)
+                b["x2"][:k].copy_(x2_host[lo:hi], non_blocking=True)
+                b["ready"].record(self.copy_in)
+            h2d += 2 * x1_host[lo:hi].numel() * 4
+            main.wait_event(b["ready"])
+            main.wait_event(b["copied"])                    # previous result of this slot has left the device
+            logits = self.model(b["x1"][:k], b["x2"][:k])
+            res = logits if self.return_logits else logits.argmax(1).to(torch.uint8)
+            b["out"] = res
+            b["done"].record(main)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(b["done"])
+                out_host[lo:hi].copy_(res, non_blocking=True)
+                b["copied"].record(self.copy_out)
+            res.record_stream(self.copy_out)
+            d2h += res.numel() * res.element_size()
+        main.wait_stream(self.copy_out)
+        return h2d, d2h
+
+
+def predict_patches(model, p1, p2, batch_size: int = 16, return_logits: bool = False,
+                    pipeline: Optional[HostPipeline] = None):
+    """Drop-in for the loop at reference train.py:187-201: ``p1``/``p2`` are host arrays [N,13,S,S] fp32 (as
+    produced by ``generate_patches``); returns the host change mask [N,S,S] uint8 (or fp32 logits)."""
+    x1 = torch.as_tensor(p1)
+    x2 = torch.as_tensor(p2)
+    if not x1.is_pinned():
+        x1, x2 = x1.pin_memory(), x2.pin_memory()
+    n, c, s, _ = x1.shape
+    if pipeline is None:
+        pipeline = HostPipeline(model, batch_size, c, s, return_logits)
+    shape = (n, 2, s, s) if return_logits else (n, s, s)
+    out = torch.empty(shape, dtype=torch.float32 if return_logits else torch.uint8).pin_memory()
+    pipeline.run(x1, x2, out)
+    torch.cuda.current_stream().synchronize()
+    return out

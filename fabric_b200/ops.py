@@ -14,6 +14,17 @@ from . import _lib
 from ._lib import Conv3x3Desc, ConvTuning, check
 
 
+# bookkeeping for bench.py: how many of OUR kernels were launched, and (optionally) CUDA-event brackets around
+# every conv launch on the launching stream so the roofline figure is measured live inside the timed region
+LAUNCHES = 0
+CONV_PROFILE = None   # set to a list to collect (tag, start_event, end_event, algorithmic_flops)
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -50,6 +61,7 @@ def pack_input(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_pad: Optio
         out = torch.empty((b, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
     assert out.shape == (b, h, w, c_pad) and out.dtype == torch.bfloat16
     check(_lib.load().fabric_b200_pack_nchw_f32_to_nhwc_bf16(_p(x), _p(out), b, c, c_pad, h, w, _stream()), "pack_input")
+    _count()
     return out
 
 
@@ -59,6 +71,7 @@ def unpack_output(x: torch.Tensor) -> torch.Tensor:
     b, h, w, c = x.shape
     out = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device)
     check(_lib.load().fabric_b200_unpack_nhwc_bf16_to_nchw_f32(_p(x), _p(out), b, c, h, w, _stream()), "unpack_output")
+    _count()
     return out
 
 
@@ -76,6 +89,7 @@ def pack_conv_weight(w: torch.Tensor, mode: int = 0) -> torch.Tensor:
         cp = cin
         out = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=w.device)
     check(_lib.load().fabric_b200_pack_conv3x3_weight(_p(w), _p(out), cout, cin, cp, mode, _stream()), "pack_conv_weight")
+    _count()
     return out
 
 
@@ -88,6 +102,7 @@ def bn_fold_eval(bn: torch.nn.BatchNorm2d, conv_bias: Optional[torch.Tensor]):
     check(_lib.load().fabric_b200_bn_fold_eval(_p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean),
                                                _p(bn.running_var), _p(None if conv_bias is None else conv_bias.detach()),
                                                float(bn.eps), _p(scale), _p(shift), c, _stream()), "bn_fold_eval")
+    _count()
     return scale, shift
 
 
@@ -100,7 +115,8 @@ DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, 
 
 def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False, pool: bool = False, stats: bool = False,
-            head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None):
+            head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None,
+            true_cin: Optional[int] = None):
     """3x3 pad-1 convolution on tcgen05 (see include/fabric_b200.h: fabric_b200_conv3x3).
 
     Returns a dict with ``y`` [G,B,H,W,cout] bf16 and optionally ``pool`` [G,B,H/2,W/2,cout],
@@ -140,7 +156,17 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
         d.stats_ws = _p(ws)
         grid = check(lib.fabric_b200_conv3x3_grid(C.byref(d)), "conv3x3 plan")
         res["stats"] = ws.view(grid, 2, -1, 2)
+    prof = CONV_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.fabric_b200_conv3x3(C.byref(d), _stream()), "conv3x3")
+    _count()
+    if prof is not None:
+        e1.record()
+        # algorithmic flops: true input channels (13, not the padded 16) -- SURVEY.md 8d
+        cin_true = true_cin if true_cin is not None else cin
+        prof.append((f"{cin_true}->{cout}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * cout))
     return res
 
 
@@ -155,6 +181,7 @@ def build_up_input(skip5: torch.Tensor, low5: torch.Tensor) -> torch.Tensor:
     out = torch.empty((1, b, h_, w_, cs + cl), dtype=torch.bfloat16, device=skip5.device)
     check(_lib.load().fabric_b200_build_up_input(_p(skip5), _p(low5), _p(out), b, h_, w_, cs, h, w, cl, lg, _stream()),
           "build_up_input")
+    _count()
     return out
 
 
@@ -166,4 +193,5 @@ def outconv(x5: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
     out = torch.empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
     check(_lib.load().fabric_b200_outconv(_p(x5), _p(weight.detach().reshape(2, c).contiguous()), _p(bias.detach()), _p(out),
                                           g * b, h, w, c, _stream()), "outconv")
+    _count()
     return out

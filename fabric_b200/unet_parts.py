@@ -83,7 +83,7 @@ class double_conv(nn.Module):
             raise NotImplementedError("training-mode forward goes through fabric_b200.autograd (double_conv_train)")
         s1, h1 = self._folded(0)
         s2, h2 = self._folded(3)
-        mid = ops.conv3x3(x5, self._packed(0), self.out_ch, s1, h1, relu=True, tune=self.tune1)["y"]
+        mid = ops.conv3x3(x5, self._packed(0), self.out_ch, s1, h1, relu=True, tune=self.tune1, true_cin=self.in_ch)["y"]
         return ops.conv3x3(mid, self._packed(3), self.out_ch, s2, h2, relu=True, pool=pool, head=head,
                            store_main=keep_main, tune=self.tune2)
 

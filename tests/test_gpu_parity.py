@@ -1,0 +1,265 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI, against
+(1) the CPU oracle on seeded inputs, (2) the committed golden fixtures the unmodified reference produced, and
+(3) size-independent properties at the BASELINE batch size.
+
+Tolerances (stated): the kernels compute in bf16 with fp32 accumulation, the oracle in fp32.
+  * one conv on bf16-rounded operands vs fp32 conv of the same operands: relative L2 <= 5e-3 (bf16 output rounding
+    is 2^-9 = 2e-3 relative per element);
+  * whole network (18 convs deep) logits vs fp32 oracle: relative L2 <= 1e-2, argmax agreement >= 99.9 %.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONV_TOL = 5e-3
+NET_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fabric_b200 import _lib
+    _lib.load()                       # the extension must be there: no silent fallback
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def conv_ref_cpu(x5, w, scale, shift, relu):
+    """oracle arithmetic (F.conv2d fp32 on CPU, reference models/unet_parts.py:13) on the bf16-rounded operands"""
+    g, b, h, wd, cp = x5.shape
+    cin = w.shape[1]
+    x = x5.reshape(g * b, h, wd, cp)[..., :cin].permute(0, 3, 1, 2).float().cpu()
+    y = F.conv2d(x, w.bfloat16().float().cpu(), None, padding=1)
+    if scale is not None:
+        y = y * scale.cpu()[None, :, None, None] + shift.cpu()[None, :, None, None]
+    return y.relu() if relu else y
+
+
+CONV_CASES = [
+    # G, B, H, W, cin, cout, tune
+    (1, 1, 16, 8, 64, 64, dict(halo=0)),
+    (1, 1, 16, 8, 64, 64, dict(halo=1)),
+    (2, 3, 20, 12, 64, 64, dict(halo=0)),            # ragged tiles: H, W not multiples of the 16x8 tile
+    (2, 3, 20, 12, 64, 64, dict(halo=1)),
+    (1, 2, 32, 32, 128, 128, dict(halo=1)),
+    (1, 2, 32, 32, 128, 256, dict(halo=1, n_tile=256)),
+    (1, 2, 32, 32, 128, 256, dict(halo=0, n_tile=128)),
+    (2, 2, 32, 32, 13, 64, dict()),                    # 13-band stem, channels padded to 16
+    (2, 3, 8, 8, 64, 128, dict()),                     # small maps: tiles span several images
+    (2, 5, 4, 4, 128, 128, dict()),
+    (2, 5, 2, 2, 128, 128, dict()),
+    (1, 2, 45, 45, 64, 128, dict(halo=1)),             # odd sizes (patch 90 path)
+    (2, 2, 5, 5, 64, 64, dict()),
+    (1, 4, 64, 64, 64, 64, dict(halo=1, b_resident=1, grid=8)),   # weights resident in smem, few persistent CTAs
+    (1, 1, 1, 1, 64, 64, dict()),                      # degenerate 1x1 map
+]
+
+
+@pytest.mark.parametrize("G,B,H,W,cin,cout,tune", CONV_CASES)
+def test_conv3x3_matches_oracle(cuda, G, B, H, W, cin, cout, tune):
+    from fabric_b200 import ops
+    torch.manual_seed(G * 1000 + H * 10 + cin)
+    cp = ops.cpad(cin)
+    x5 = torch.zeros(G, B, H, W, cp, device=cuda, dtype=torch.bfloat16)
+    x5[..., :cin] = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5)
+    scale = 0.5 + torch.rand(cout, device=cuda)
+    shift = 0.3 * torch.randn(cout, device=cuda)
+    res = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), cout, scale, shift, relu=True, tune=tune)
+    y = res["y"].reshape(G * B, H, W, cout).permute(0, 3, 1, 2).float().cpu()
+    ref = conv_ref_cpu(x5, w, scale, shift, True)
+    assert rel(y, ref) < CONV_TOL
+    assert (y - ref).abs().max() <= 2 ** -7 * ref.abs().max() + 1e-6
+
+
+@pytest.mark.parametrize("halo", [0, 1])
+def test_conv3x3_fused_pool_stats_head(cuda, halo):
+    from fabric_b200 import ops
+    torch.manual_seed(3)
+    G, B, H, W, cin, cout = 2, 2, 45, 45, 64, 64
+    x5 = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5)
+    hw, hb = torch.randn(2, cout, device=cuda) * 0.2, torch.randn(2, device=cuda)
+    res = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), cout, None, None, relu=False, pool=True, stats=True,
+                      head=(hw, hb), tune=dict(halo=halo))
+    ref = conv_ref_cpu(x5, w, None, None, False)
+    refq = ref.bfloat16().float()            # the stored activation is bf16; fused consumers see the stored value
+    y = res["y"].reshape(G * B, H, W, cout).permute(0, 3, 1, 2).float().cpu()
+    assert rel(y, ref) < CONV_TOL
+    # nn.MaxPool2d(2) (floor) of the stored tensor: exact
+    pool = res["pool"].reshape(G * B, H // 2, W // 2, cout).permute(0, 3, 1, 2).float().cpu()
+    assert torch.equal(pool, F.max_pool2d(y, 2))
+    # BatchNorm moments per date group of the stored tensor
+    st = res["stats"].double().cpu()
+    tot = st.sum(0)                          # one N tile -> every CTA holds the same channels
+    yq = y.reshape(G, B, cout, H, W).double()
+    assert torch.allclose(tot[:, :, 0], yq.sum(dim=(1, 3, 4)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[:, :, 1], (yq * yq).sum(dim=(1, 3, 4)), rtol=1e-4, atol=1e-2)
+    # fused 1x1 head on the stored tensor
+    lr = torch.einsum("nchw,kc->nkhw", y, hw.cpu()) + hb.cpu()[None, :, None, None]
+    assert rel(res["logits"].cpu(), lr) < 1e-4
+    del refq
+
+
+def test_conv3x3_linearity_and_halo_equals_tap(cuda):
+    """conv(2x) == 2 conv(x) exactly (power-of-two scaling commutes with bf16/fp32 rounding) and the two operand
+    feeding modes give bit-identical results (same products, same accumulation order)."""
+    from fabric_b200 import ops
+    torch.manual_seed(5)
+    x5 = torch.randn(1, 2, 48, 40, 128, device=cuda).bfloat16()
+    wp = ops.pack_conv_weight(torch.randn(128, 128, 3, 3, device=cuda) / 30, 0)
+    a = ops.conv3x3(x5, wp, 128, tune=dict(halo=1))["y"]
+    b = ops.conv3x3(x5 * 2, wp, 128, tune=dict(halo=1))["y"]
+    c = ops.conv3x3(x5, wp, 128, tune=dict(halo=0))["y"]
+    assert torch.equal(a.float() * 2, b.float())
+    assert torch.equal(a, c)
+
+
+def test_pack_unpack_roundtrip(cuda):
+    from fabric_b200 import ops
+    x = torch.randn(3, 13, 37, 70, device=cuda)
+    p = ops.pack_input(x)
+    assert p.shape == (3, 37, 70, 16) and p.dtype == torch.bfloat16
+    assert torch.equal(p[..., :13].permute(0, 3, 1, 2).float(), x.bfloat16().float())
+    assert torch.count_nonzero(p[..., 13:]) == 0
+    y = torch.randn(2, 19, 33, 64, device=cuda).bfloat16()
+    assert torch.equal(ops.unpack_output(y), y.permute(0, 3, 1, 2).float())
+
+
+@pytest.mark.parametrize("H,W,h,w,lg", [(32, 32, 16, 16, 2), (11, 11, 5, 5, 1), (45, 45, 22, 22, 1), (8, 8, 4, 4, 2)])
+def test_build_up_input_matches_oracle(cuda, H, W, h, w, lg):
+    """relu(d2*d1) skip + bilinear(align_corners=True) x2 + F.pad + cat -- reference bidate_model.py:35-38,
+    unet_parts.py:56-58,65-78"""
+    from fabric_b200 import ops
+    torch.manual_seed(7)
+    B, Cs, Cl = 2, 64, 128
+    skip = torch.randn(2, B, H, W, Cs, device=cuda).relu().bfloat16()
+    low = torch.randn(lg, B, h, w, Cl, device=cuda).relu().bfloat16()
+    out = ops.build_up_input(skip, low)[0].float().cpu()
+    s = skip.float().cpu()
+    lo = low.float().cpu()
+    lo = torch.relu(lo[0] * lo[1]) if lg == 2 else lo[0]
+    x1 = F.interpolate(lo.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = H - x1.shape[2], W - x1.shape[3]
+    x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    ref = torch.cat([torch.relu(s[1] * s[0]).permute(0, 3, 1, 2), x1], 1).permute(0, 2, 3, 1)
+    assert rel(out, ref) < 3e-3
+    assert (out - ref).abs().max() <= 2 ** -7 * ref.abs().max()
+
+
+def _model(cuda, sd):
+    from fabric_b200 import BiDateNet
+    m = BiDateNet(13, 2)
+    m.load_state_dict(sd)
+    return m.to(cuda).eval()
+
+
+@pytest.mark.parametrize("key,fuse", [("c1", True), ("c1", False), ("p90", True), ("p90", False)])
+def test_eval_forward_matches_reference_golden(cuda, golden, key, fuse):
+    """config 1 (B=2, 13x32x32) and the reference's default patch 90 (F.pad branch), against the logits the
+    unmodified reference produced."""
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, O.make_state_dict(seed=0))
+    model.fuse_head = fuse
+    with torch.no_grad():
+        out = model(golden[f"{key}_x1"].to(cuda), golden[f"{key}_x2"].to(cuda)).cpu()
+    ref = golden[f"{key}_logits_eval"]
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel(out, ref) < NET_TOL
+    assert (out.argmax(1) == ref.argmax(1)).float().mean() >= 0.999
+
+
+def test_eval_forward_256_matches_golden_and_oracle(cuda, golden):
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    x1, x2, _ = O.make_inputs(1, 256, seed=3)
+    assert torch.allclose(x1.double().sum(), golden["p256_x1_sum"])
+    model = _model(cuda, sd)
+    with torch.no_grad():
+        out = model(x1.to(cuda), x2.to(cuda)).cpu()
+    ref = golden["p256_logits_eval"]
+    assert rel(out, ref) < NET_TOL
+    assert (out.argmax(1) == ref.argmax(1)).float().mean() >= 0.999
+
+
+def test_encoder_blocks_match_oracle(cuda):
+    """per-block parity (standalone NCHW fp32 entry points of the mirrored modules) vs the oracle"""
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    model = _model(cuda, sd)
+    x1, _, _ = O.make_inputs(2, 32, seed=11)
+    with torch.no_grad():
+        a = model.inc(x1.to(cuda)).cpu()
+        ref_a = O.inconv(x1, sd)
+        assert rel(a, ref_a) < 5e-3
+        b = model.down1(ref_a.to(cuda)).cpu()
+        assert rel(b, O.down(ref_a, sd, "down1")) < 5e-3
+        lo = O.down(ref_a, sd, "down1")
+        u = model.up4  # up(128, 64): skip 64 ch @32, low 64 ch @16
+        low = torch.rand(2, 64, 16, 16)
+        skip = torch.rand(2, 64, 32, 32)
+        c = u(low.to(cuda), skip.to(cuda)).cpu()
+        assert rel(c, O.up(low, skip, sd, "up4")) < 5e-3
+        lg = model.outc(skip.to(cuda)).cpu()
+        assert rel(lg, O.outconv(skip, sd)) < 5e-3
+    del lo
+
+
+def test_full_batch_properties(cuda):
+    """BASELINE size (64 pairs of 13x256x256): properties that need no oracle run.
+    (a) a pair's logits do not depend on its batch neighbours (eval mode): bit-exact vs running it alone;
+    (b) the network is symmetric in its two dates (shared encoder, product fusion): bit-exact swap."""
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, O.make_state_dict(seed=0))
+    g = torch.Generator(device=cuda).manual_seed(5)
+    x1 = torch.randn(64, 13, 256, 256, device=cuda, generator=g)
+    x2 = torch.randn(64, 13, 256, 256, device=cuda, generator=g)
+    with torch.no_grad():
+        full = model(x1, x2)
+        assert full.shape == (64, 2, 256, 256)
+        assert torch.isfinite(full).all()
+        for i in (0, 17, 63):
+            assert torch.equal(model(x1[i:i + 1], x2[i:i + 1])[0], full[i])
+        assert torch.equal(model(x2, x1), full)
+        # and one pair of the big batch against the fp32 oracle
+        ref = O.bidatenet_forward(x1[5:6].cpu(), x2[5:6].cpu(), O.make_state_dict(seed=0))
+        assert rel(full[5:6].cpu(), ref) < NET_TOL
+
+
+def test_state_dict_and_pickle_roundtrip_on_device(cuda, tmp_path):
+    """train.py:222 pickles the whole model; reloading must give identical logits"""
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, O.make_state_dict(seed=0))
+    x1, x2, _ = O.make_inputs(1, 32, seed=4)
+    with torch.no_grad():
+        a = model(x1.to(cuda), x2.to(cuda))
+    p = tmp_path / "ckpt.pt"
+    torch.save(model, p)
+    m2 = torch.load(p, weights_only=False)
+    with torch.no_grad():
+        b = m2(x1.to(cuda), x2.to(cuda))
+    assert torch.equal(a, b)
+
+
+def test_host_pipeline_matches_direct_call(cuda):
+    from fabric_b200.inference import predict_patches
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, O.make_state_dict(seed=0))
+    x1, x2, _ = O.make_inputs(5, 64, seed=6)
+    with torch.no_grad():
+        direct = model(x1.to(cuda), x2.to(cuda)).cpu()
+    logits = predict_patches(model, x1.numpy(), x2.numpy(), batch_size=2, return_logits=True)
+    assert torch.equal(logits, direct)
+    mask = predict_patches(model, x1.numpy(), x2.numpy(), batch_size=2, return_logits=False)
+    assert torch.equal(mask, direct.argmax(1).to(torch.uint8))
