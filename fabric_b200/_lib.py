@@ -35,8 +35,13 @@ class Conv3x3Desc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [("G", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ca", C.c_int), ("Cb", C.c_int),
+                ("p", C.c_void_p), ("q", C.c_void_p), ("ws", C.c_void_p), ("splits", C.c_int), ("wide", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/fabric_b200.h
-_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 SIGNATURES = {
     "fabric_b200_version": (_i, []),
     "fabric_b200_last_error": (C.c_char_p, []),
@@ -50,6 +55,20 @@ SIGNATURES = {
     "fabric_b200_bn_fold_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     "fabric_b200_build_up_input": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_outconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_finalize": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "fabric_b200_bn_apply_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_seg_loss_ws_floats": (_i64, [_i, _i, _i]),
+    "fabric_b200_seg_loss_fwd_bwd": (_i, [_i, _f, _f, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fabric_b200_outconv_bwd_ws_floats": (_i64, [_i]),
+    "fabric_b200_outconv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_bwd_ws_floats": (_i64, [_i, _i]),
+    "fabric_b200_bn_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_up_input_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_conv3x3_wgrad_ws_floats": (_i64, [C.POINTER(WgradDesc)]),
+    "fabric_b200_conv3x3_wgrad_splits": (_i, [C.POINTER(WgradDesc)]),
+    "fabric_b200_conv3x3_wgrad": (_i, [C.POINTER(WgradDesc), _vp]),
+    "fabric_b200_wgrad_reduce": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -168,15 +168,6 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
   shift[c] = ((bias ? bias[c] : 0.f) - rm[c]) * s + beta[c];
 }
 
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  f[0] = fb::bf16_lo(v.x), f[1] = fb::bf16_hi(v.x), f[2] = fb::bf16_lo(v.y), f[3] = fb::bf16_hi(v.y);
-  f[4] = fb::bf16_lo(v.z), f[5] = fb::bf16_hi(v.z), f[6] = fb::bf16_lo(v.w), f[7] = fb::bf16_hi(v.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(fb::pack_bf16x2(f[0], f[1]), fb::pack_bf16x2(f[2], f[3]), fb::pack_bf16x2(f[4], f[5]),
-                    fb::pack_bf16x2(f[6], f[7]));
-}
-
 // decoder input: [skip_d1 * skip_d2 | bilinear x2 (align_corners) of low, zero padded]; one thread = 8 channels
 __global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ low, uint4* __restrict__ out,
                                       int B, int H, int W, int Cs, int h, int w, int Cl, int low_groups) {
@@ -198,8 +189,8 @@ __global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint
     if (c8 < Cs8) {
       const size_t o = (((size_t)b * H + y) * W + x) * Cs8 + c8;
       float a[8], c[8];
-      unpack8(skip[o], a);
-      unpack8(skip[o + skip_g], c);
+      fb::unpack8(skip[o], a);
+      fb::unpack8(skip[o + skip_g], c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = fmaxf(a[j] * c[j], 0.f);
     } else {
@@ -218,10 +209,10 @@ __global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint
         for (int t = 0; t < 4; ++t) {
           const size_t o = (((size_t)b * h + ys[t]) * w + xs[t]) * Cl8 + cl;
           float a[8];
-          unpack8(low[o], a);
+          fb::unpack8(low[o], a);
           if (low_groups == 2) {
             float c[8];
-            unpack8(low[o + low_g], c);
+            fb::unpack8(low[o + low_g], c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * c[j], 0.f);
           }
@@ -230,7 +221,7 @@ __global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint
         }
       }
     }
-    out[i] = pack8(r);
+    out[i] = fb::pack8(r);
   }
 }
 
@@ -248,7 +239,7 @@ __global__ void outconv_kernel(const uint4* __restrict__ x, const float* __restr
     const uint4* row = x + pix * C8;
     for (int c8 = 0; c8 < C8; ++c8) {
       float f[8];
-      unpack8(row[c8], f);
+      fb::unpack8(row[c8], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a0 = fmaf(f[j], sw[c8 * 8 + j], a0);

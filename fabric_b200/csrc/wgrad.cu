@@ -1,0 +1,101 @@
+// Host side of the tcgen05 weight-gradient kernel (see wgrad_umma.cuh, include/fabric_b200.h).
+#include "host_common.cuh"
+#include "wgrad_umma.cuh"
+
+using namespace fbh;
+
+namespace {
+
+struct WgPlan {
+  fb::WgradParams p;
+  int qck, grid, smem, wide;
+};
+
+int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
+  if (!d) return fail(FB_ERR_ARG, "null descriptor");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (d->G < 1 || d->G > 2 || d->B < 1 || d->H < 1 || d->W < 1) return fail(FB_ERR_SHAPE, "bad G/B/H/W");
+  if (d->Ca <= 0 || d->Ca % 64) return fail(FB_ERR_SHAPE, "Ca %d must be a multiple of 64", d->Ca);
+  if (!(d->Cb == 16 || (d->Cb > 0 && d->Cb % 64 == 0))) return fail(FB_ERR_SHAPE, "Cb %d must be 16 or k*64", d->Cb);
+  fb::WgradParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.G = d->G, p.B = d->B, p.H = d->H, p.W = d->W, p.Ca = d->Ca, p.Cb = d->Cb;
+  if (d->H > 8) p.bh = 16;
+  else if (d->H > 4) p.bh = 8;
+  else if (d->H > 2) p.bh = 4;
+  else p.bh = 2;
+  p.bn = 16 / p.bh;
+  p.tiles_x = (d->W + 7) / 8;
+  p.tiles_y = (d->H + p.bh - 1) / p.bh;
+  p.tiles_b = (d->B + p.bn - 1) / p.bn;
+  p.tiles_total = p.tiles_x * p.tiles_y * p.tiles_b * d->G;
+  pl->qck = d->Cb == 16 ? 16 : 64;
+  p.m_tiles = (d->Ca + 127) / 128;
+  p.n_chunks = d->Cb / pl->qck;
+  const int items = p.m_tiles * p.n_chunks * 3;
+  int splits = d->splits;
+  if (splits <= 0) {
+    splits = (2 * di.sms + items - 1) / items;
+    const int max_splits = p.tiles_total / 4 > 0 ? p.tiles_total / 4 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  const int stage = fb::wg_stage_bytes(pl->qck);
+  int stages = (di.smem_optin - 2048) / stage;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(FB_ERR_SHAPE, "not enough shared memory");
+  p.stages = stages;
+  pl->smem = stages * stage + 2048;
+  pl->grid = items * splits;
+  pl->wide = d->wide != 0;
+  p.ws = d->ws;
+  return FB_OK;
+}
+
+template <int QCK, bool WIDE>
+int launch_wgrad(const WgPlan& pl, const CUtensorMap& tP, const CUtensorMap& tQ, cudaStream_t st) {
+  auto k = fb::wgrad_umma_kernel<QCK, WIDE>;
+  FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+  k<<<pl.grid, fb::kWgThreads, pl.smem, st>>>(tP, tQ, pl.p);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t fabric_b200_conv3x3_wgrad_ws_floats(const fb_wgrad_desc* d) {
+  WgPlan pl;
+  int rc = plan_wgrad(d, &pl);
+  return rc ? rc : (int64_t)pl.p.splits * d->Ca * 9 * d->Cb;
+}
+
+int fabric_b200_conv3x3_wgrad_splits(const fb_wgrad_desc* d) {
+  WgPlan pl;
+  int rc = plan_wgrad(d, &pl);
+  return rc ? rc : pl.p.splits;
+}
+
+int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream) {
+  WgPlan pl;
+  int rc = plan_wgrad(d, &pl);
+  if (rc) return rc;
+  if (!d->p || !d->q || !d->ws) return fail(FB_ERR_ARG, "null tensor pointer");
+  if (!aligned16(d->p) || !aligned16(d->q) || !aligned16(d->ws)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
+  const fb::WgradParams& p = pl.p;
+  CUtensorMap tP, tQ;
+  rc = make_tmap_act(&tP, d->p, p.Ca, p.W, p.H, p.B, p.G, 64, 8, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, pl.qck, 10, p.bh, p.bn,
+                     pl.qck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl.qck == 64) return pl.wide ? launch_wgrad<64, true>(pl, tP, tQ, st) : launch_wgrad<64, false>(pl, tP, tQ, st);
+  return pl.wide ? launch_wgrad<16, true>(pl, tP, tQ, st) : launch_wgrad<16, false>(pl, tP, tQ, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// Weight gradient of the 3x3 convolution on tcgen05 tensor cores (sm_100a).
+//
+//   dW[ca][tap][cb] = sum over pixels  P[pix][ca] * Q[pix + tap][cb]        P = dL/d(conv output), Q = conv input
+//
+// (autograd of nn.Conv2d, reference train.py:94 -> models/unet_parts.py:13,16).  The reduction runs over PIXELS, so
+// both GEMM operands are "MN-major": the NHWC tiles land in shared memory by TMA exactly as they lie in HBM
+// ([pixel][64 channels], 128B swizzle) and the UMMA descriptors read them with the channel index as the fast M/N
+// dimension and 8-pixel groups as the K dimension -- no transpose pass anywhere.
+//
+// Work item = (128 P-channels, 64 Q-channels, filter row r, K split): three accumulators (filter columns s=0..2) of
+// 128 x 64 fp32 in TMEM.  The Q tile is loaded once per pixel tile WITH its horizontal halo (10 pixels per row, row
+// y0+r-1 chosen by the TMA coordinate), and the three filter columns are three descriptors into that buffer (start
+// address + s pixels, stride-byte-offset = 10 pixels), as in the forward HALO mode.
+// WIDE mode issues ONE N=192 MMA instead of three N=64 ones: the three 64-channel N atoms are the same buffer at
+// leading-byte-offset = 1 pixel (overlapping atoms), which halves the A-operand shared-memory reads.
+#pragma once
+#include "ptx.cuh"
+
+namespace fb {
+
+struct WgradParams {
+  int G, B, H, W;
+  int Ca, Cb;   // channels of P (rows of dW) and of Q (padded to a multiple of 64)
+  int bh, bn;   // pixel tile = bn images x bh rows x 8 columns (bh * bn == 16)
+  int tiles_x, tiles_y, tiles_b;
+  int m_tiles, n_chunks, splits;
+  int tiles_total;  // pixel tiles = G * tiles_b * tiles_y * tiles_x
+  int stages;
+  float* ws;  // [splits][Ca][9][Cb] fp32 partial sums
+};
+
+constexpr int kWgThreads = 192;
+constexpr int kWgPBytes = 2 * 16384;             // two 64-channel atoms of 128 pixels
+// Q stage: 160 pixel slots (16 rows x 10 columns) x QCK channels; QCK = 16 is the 13-band stem (32B swizzle)
+__host__ __device__ constexpr int wg_q_bytes(int QCK) { return 160 * QCK * 2; }
+__host__ __device__ constexpr int wg_stage_bytes(int QCK) { return kWgPBytes + wg_q_bytes(QCK); }
+
+template <int QCK, bool WIDE>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgradParams p) {
+  static_assert(QCK == 64 || QCK == 16, "Q channel chunk");
+  constexpr int kWgStage = wg_stage_bytes(QCK);
+  constexpr uint32_t PIX = QCK * 2;                 // bytes per pixel of the Q tile
+  constexpr uint32_t Q_LAYOUT = QCK == 64 ? kLayoutSw128 : kLayoutSw32;
+  constexpr int NQ = QCK;                           // N per filter column
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+  const uint32_t bar_off = p.stages * kWgStage;
+  const uint32_t bars = base + bar_off;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (p.stages + s); };
+  const uint32_t done_bar = bars + 8u * (2 * p.stages);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item
+  int it = blockIdx.x;
+  const int split = it % p.splits;
+  it /= p.splits;
+  const int r = it % 3;
+  it /= 3;
+  const int nc = it % p.n_chunks;
+  const int mt = it / p.n_chunks;
+  const int t_begin = (int)((long long)p.tiles_total * split / p.splits);
+  const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP);
+    prefetch_tmap(&tmQ);
+  }
+  if (warp == 1) {
+    tmem_alloc(base + bar_off + 512, 256);
+    tmem_relinquish();
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full(s), 1);
+        mbar_init(empty(s), 1);
+      }
+      mbar_init(done_bar, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      int m = t;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      m /= p.tiles_y;
+      const int tb = m % p.tiles_b;
+      const int g = m / p.tiles_b;
+      const int x0 = tx * 8, y0 = ty * p.bh, b0 = tb * p.bn;
+      mbar_wait(empty(stage), phase ^ 1);
+      if (elect_one()) {
+        const uint32_t dst = base + stage * kWgStage;
+        mbar_arrive_expect_tx(full(stage), kWgStage);  // P: 2 x 16 KB, Q: 160 pixel slots
+        tma_load_5d(dst, &tmP, full(stage), mt * 128, x0, y0, b0, g);
+        tma_load_5d(dst + 16384, &tmP, full(stage), mt * 128 + 64, x0, y0, b0, g);  // beyond Ca: zero filled
+        tma_load_5d(dst + kWgPBytes, &tmQ, full(stage), nc * QCK, x0 - 1, y0 + r - 1, b0, g);
+      }
+      __syncwarp();
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else if (warp == 1) {
+    // A: M = P channels (MN-major), 2 atoms of 64 at LBO = 16384, K groups of 8 pixels at SBO = 1024
+    // B: N = Q channels (MN-major), K groups of 8 pixels at SBO = 1280 (one halo row of 10 pixels)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, WIDE ? 3 * NQ : NQ, 1, 1);
+    constexpr uint32_t B_LBO = WIDE ? PIX : 16384;   // WIDE: the next N atom is the same buffer one pixel further
+    constexpr uint32_t B_SBO = 10 * PIX;             // 8-pixel K group stride = one halo row
+    constexpr uint64_t a_hi = umma_desc(0, 16384, 1024, kLayoutSw128) & 0xFFFFFFFF00000000ull;
+    constexpr uint64_t b_hi = umma_desc(0, B_LBO, B_SBO, Q_LAYOUT) & 0xFFFFFFFF00000000ull;
+    constexpr uint32_t a_lo_fixed = static_cast<uint32_t>(umma_desc(0, 16384, 0, 0) & 0xFFFFFFFFu);
+    constexpr uint32_t b_lo_fixed = static_cast<uint32_t>(umma_desc(0, B_LBO, 0, 0) & 0xFFFFFFFFu);
+    constexpr uint32_t B_JSTEP = (2 * B_SBO) >> 4, B_SSTEP = PIX >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(full(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo_fixed + ((base + stage * kWgStage) >> 4);
+        const uint32_t b_lo = b_lo_fixed + ((base + stage * kWgStage + kWgPBytes) >> 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 16 pixels (two tile rows) per MMA
+          if constexpr (WIDE) {
+            umma_bf16(tmem_base, a_hi | (a_lo + j * 128), b_hi | (b_lo + j * B_JSTEP), idesc, accumulate);
+          } else {
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              umma_bf16(tmem_base + s * NQ, a_hi | (a_lo + j * 128), b_hi | (b_lo + j * B_JSTEP + s * B_SSTEP), idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit(empty(stage));
+        if (t == t_end - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else {
+    // epilogue: 128 rows (P channels) x 3 taps x 64 Q channels -> fp32 partial slab of this split
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ca = mt * 128 + row;
+    if (t_end > t_begin) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int s = 0; s < 3; ++s) {
+#pragma unroll 1
+      for (int cc = 0; cc < (NQ + 31) / 32; ++cc) {
+        uint32_t v[32];
+        if (t_end > t_begin) {
+          // (for NQ = 16 this reads 16 columns past the tap's accumulator; they are simply not stored)
+          tmem_ld_32x32(tmem_base + s * NQ + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (ca < p.Ca) {
+          float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)split * p.Ca + ca) * 9 + (r * 3 + s)) * p.Cb + nc * QCK + cc * 32);
+#pragma unroll
+          for (int i = 0; i < (NQ < 32 ? NQ : 32) / 4; ++i)
+            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace fb

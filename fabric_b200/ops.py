@@ -195,3 +195,129 @@ def outconv(x5: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
                                           g * b, h, w, c, _stream()), "outconv")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training ops
+WGRAD_WIDE = 1   # one N=3*64 MMA per K step (overlapping N atoms one pixel apart); validated bit-level against the 3-MMA form
+
+
+def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_per_group: int, groups: int):
+    """Finish train-mode BatchNorm from the conv epilogue's moment partials; updates the running statistics in
+    place (momentum, unbiased variance, num_batches_tracked += groups).  Returns (scale, shift, mean, invstd) [G,C]."""
+    grid, _, n_tile, _ = stats.shape
+    c = bn.num_features
+    dev = stats.device
+    out = [torch.empty((groups, c), dtype=torch.float32, device=dev) for _ in range(4)]
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    check(_lib.load().fabric_b200_bn_finalize(_p(stats), grid, n_tile, c, groups, int(count_per_group),
+                                              _p(None if conv_bias is None else conv_bias.detach()), _p(bn.weight.detach()),
+                                              _p(bn.bias.detach()), _p(bn.running_mean), _p(bn.running_var),
+                                              _p(bn.num_batches_tracked), mom, float(bn.eps), _p(out[0]), _p(out[1]),
+                                              _p(out[2]), _p(out[3]), _stream()), "bn_finalize")
+    _count()
+    # the kernel wrote the running statistics behind torch's back: invalidate caches keyed on tensor versions
+    bn.__dict__["_fb_stats_epoch"] = bn.__dict__.get("_fb_stats_epoch", 0) + 1
+    return out
+
+
+def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, pool: bool = False):
+    g, b, h, w, c = z5.shape
+    a = torch.empty_like(z5)
+    pl = torch.empty((g, b, h // 2, w // 2, c), dtype=torch.bfloat16, device=z5.device) if pool else None
+    check(_lib.load().fabric_b200_bn_apply_relu(_p(z5), _p(scale), _p(shift), _p(a), _p(pl), g, b, h, w, c, _stream()),
+          "bn_apply_relu")
+    _count()
+    return a, pl
+
+
+LOSS_KINDS = {"tversky": 0, "dice": 1, "jaccard": 2, "focal": 3, "ce": 4, "bce": 4}
+
+
+def seg_loss_fwd_bwd(kind: str, logits: torch.Tensor, labels: torch.Tensor, alpha=0.5, beta=0.5, gamma=0.0, eps=1e-7):
+    """Fused loss value + dL/dlogits (utils/metrics.py).  logits [B,2,H,W] fp32, labels [B,H,W] or [B,1,H,W] int64."""
+    _need_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and logits.shape[1] == 2, "the fused losses are built for n_classes == 2"
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    b, _, h, w = logits.shape
+    nd = labels.dim()
+    if kind in ("focal", "ce", "bce"):
+        nd = 3 if nd not in (3, 4) else nd
+    assert labels.numel() == b * h * w
+    lib = _lib.load()
+    ws = torch.empty(check(lib.fabric_b200_seg_loss_ws_floats(b, h, w), "seg_loss ws"), dtype=torch.float32, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    check(lib.fabric_b200_seg_loss_fwd_bwd(LOSS_KINDS[kind], float(alpha), float(beta), float(gamma), float(eps), _p(logits),
+                                           _p(labels), nd, b, h, w, _p(loss), _p(dlogits), _p(ws), _stream()), "seg_loss")
+    _count(3)
+    return loss, dlogits
+
+
+def outconv_bwd(dlogits: torch.Tensor, u5: torch.Tensor, weight: torch.Tensor):
+    g, b, h, w, c = u5.shape
+    lib = _lib.load()
+    ws = torch.empty(check(lib.fabric_b200_outconv_bwd_ws_floats(c), "outconv_bwd ws"), dtype=torch.float32, device=u5.device)
+    du = torch.empty_like(u5)
+    dw = torch.empty((2, c), dtype=torch.float32, device=u5.device)
+    db = torch.empty((2,), dtype=torch.float32, device=u5.device)
+    check(lib.fabric_b200_outconv_bwd(_p(dlogits), _p(u5), _p(weight.detach().reshape(2, c).contiguous()), _p(du), _p(dw),
+                                      _p(db), _p(ws), g * b, h, w, c, _stream()), "outconv_bwd")
+    _count(2)
+    return du, dw.view(2, c, 1, 1), db
+
+
+def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma):
+    """BatchNorm(train)+ReLU backward with fused product / max-pool adjoints (see include/fabric_b200.h).
+    Returns (dz [G,B,H,W,C] bf16, dgamma [C], dbeta [C])."""
+    g, b, h, w, c = z5.shape
+    lib = _lib.load()
+    ws = torch.empty(check(lib.fabric_b200_bn_bwd_ws_floats(g, c), "bn_bwd ws"), dtype=torch.float32, device=z5.device)
+    dz = torch.empty_like(z5)
+    dgamma = torch.empty(c, dtype=torch.float32, device=z5.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=z5.device)
+    ga_groups, ga_ch = (ga.shape[0], ga.shape[4]) if ga is not None else (1, c)
+    check(lib.fabric_b200_bn_relu_bwd(_p(z5), _p(a5), _p(ga), ga_groups, ga_ch, int(mul_other), _p(gp), _p(scale), _p(shift),
+                                      _p(mean), _p(invstd), _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws),
+                                      g, b, h, w, c, _stream()), "bn_relu_bwd")
+    _count(3)
+    return dz, dgamma, dbeta
+
+
+def up_input_bwd(dcat5: torch.Tensor, cs: int, h: int, w: int) -> torch.Tensor:
+    _, b, hh, ww, ct = dcat5.shape
+    cl = ct - cs
+    dlow = torch.empty((1, b, h, w, cl), dtype=torch.bfloat16, device=dcat5.device)
+    check(_lib.load().fabric_b200_up_input_bwd(_p(dcat5), _p(dlow), b, hh, ww, cs, h, w, cl, _stream()), "up_input_bwd")
+    _count()
+    return dlow
+
+
+def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: int = 0, wide=None) -> torch.Tensor:
+    """dW [Cout,Cin,3,3] fp32 = autograd weight gradient of conv3x3(x5, W) given dL/dz (tcgen05, split-K)."""
+    lib = _lib.load()
+    _need_cuda(dz5, x5)
+    g, b, h, w, ca = dz5.shape
+    cb = x5.shape[4]
+    d = _lib.WgradDesc()
+    d.G, d.B, d.H, d.W, d.Ca, d.Cb = g, b, h, w, ca, cb
+    d.p, d.q = _p(dz5), _p(x5)
+    d.splits = splits
+    d.wide = WGRAD_WIDE if wide is None else int(wide)
+    d.ws = 16  # planner only checks alignment/non-null later
+    n = check(lib.fabric_b200_conv3x3_wgrad_ws_floats(C.byref(d)), "wgrad plan")
+    s = check(lib.fabric_b200_conv3x3_wgrad_splits(C.byref(d)), "wgrad plan")
+    ws = torch.empty(n, dtype=torch.float32, device=dz5.device)
+    d.ws = _p(ws)
+    prof = CONV_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib.fabric_b200_conv3x3_wgrad(C.byref(d), _stream()), "conv3x3_wgrad")
+    if prof is not None:
+        e1.record()
+        prof.append((f"wgrad {cin_true}->{ca}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * ca))
+    dw = torch.empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
+    check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
+    _count(2)
+    return dw

@@ -24,8 +24,8 @@ class _PackCache:
     def __init__(self):
         self._store = {}
 
-    def get(self, key, tensors, build):
-        sig = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+    def get(self, key, tensors, build, extra=None):
+        sig = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None) + (extra,)
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -73,7 +73,7 @@ class double_conv(nn.Module):
     def _folded(self, idx):
         conv, bn = self.conv[idx], self.conv[idx + 1]
         return self._cache().get(("bn", idx), [bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias],
-                                 lambda: ops.bn_fold_eval(bn, conv.bias))
+                                 lambda: ops.bn_fold_eval(bn, conv.bias), extra=bn.__dict__.get("_fb_stats_epoch", 0))
 
     def run5(self, x5, pool=False, head=None, keep_main=True):
         """NHWC5 bf16 in -> dict(y=..., pool=..., logits=...).  Eval mode: BatchNorm (running statistics), the conv

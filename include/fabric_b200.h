@@ -110,6 +110,71 @@ int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int
 int fabric_b200_outconv(const void* x, const float* w, const float* b, float* logits, int B, int H, int W, int C,
                         void* stream);
 
+/* ---- training: BatchNorm batch statistics ----------------------------------------------------------------- */
+
+/* nn.BatchNorm2d in training mode (unet_parts.py:14,17), finishing the moment partials the conv epilogue wrote
+ * (stats_ws of fabric_b200_conv3x3, launched with `grid` CTAs and N tile `n_tile`).  Per date group g:
+ *   mean_g, var_g (biased) -> scale[g][c] = gamma*invstd, shift[g][c] = beta - mean*scale  (conv bias cancels),
+ *   running_mean/var updated with momentum (unbiased variance, conv bias added to the mean), group 0 first then
+ *   group 1 (the reference runs date 1, then date 2); num_batches_tracked += G. */
+int fabric_b200_bn_finalize(const float* stats_ws, int grid, int n_tile, int C, int G, int64_t count_per_group,
+                            const float* conv_bias, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* scale,
+                            float* shift, float* mean, float* invstd, void* stream);
+/* a = relu(z*scale[g] + shift[g]) bf16 NHWC5, optional fused MaxPool2d(2) copy */
+int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, int G, int B,
+                              int H, int W, int C, void* stream);
+
+/* ---- training: losses (utils/metrics.py) --------------------------------------------------------------------- */
+
+/* kind: 0 tversky(alpha,beta) :130-171, 1 dice :51-83, 2 jaccard :86-119, 3 focal(gamma) :19-48,
+ * 4 softmax cross entropy (working stand-in for the reference's broken `bce`, utils/helpers.py:303-304).
+ * logits NCHW fp32 [B][2][H][W], labels int64 [B][H][W]; label_ndim 3 or 4 selects the reference's `dims`
+ * behaviour (3-D labels reduce over batch and H only).  Writes the scalar loss and dL/dlogits. */
+int64_t fabric_b200_seg_loss_ws_floats(int B, int H, int W);
+int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma, float eps, const float* logits,
+                                 const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
+                                 float* ws, void* stream);
+
+/* ---- training: backward ----------------------------------------------------------------------------------------- */
+
+/* outconv backward: du = dlogits^T W (bf16 NHWC), dw [2][C], db [2] */
+int64_t fabric_b200_outconv_bwd_ws_floats(int C);
+int fabric_b200_outconv_bwd(const float* dlogits, const void* u, const float* w, void* du, float* dw, float* db, float* ws,
+                            int B, int H, int W, int C, void* stream);
+
+/* BatchNorm(train) + ReLU backward, with the adjoints of the ops that consume the activation fused into the read:
+ *   dy = relu'(z*scale+shift) * [ ga * (mul_other ? a[other date] : 1)  +  maxpool-unpool(gp) ]
+ *   dz = gamma*invstd * (dy - mean(dy) - xhat*mean(dy*xhat)),   dgamma = sum dy*xhat,  dbeta = sum dy
+ * ga: bf16 [ga_groups][B][H][W][ga_channels] (first C channels used; ga_groups 1 = shared by both dates),
+ * mul_other: product fusion relu(d2*d1) adjoint (bidate_model.py:35-38); gp: bf16 [G][B][H/2][W/2][C] gradient of
+ * the pooled copy, routed to the first maximum of each 2x2 window like nn.MaxPool2d. */
+int64_t fabric_b200_bn_bwd_ws_floats(int G, int C);
+int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga_groups, int ga_channels, int mul_other,
+                            const void* gp, const float* scale, const float* shift, const float* mean, const float* invstd,
+                            const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws, int G, int B, int H, int W,
+                            int C, void* stream);
+
+/* adjoint of the upsample half of fabric_b200_build_up_input: dcat [B][H][W][Cs+Cl] -> dlow [B][h][w][Cl] */
+int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream);
+
+/* weight gradient of the 3x3 conv on tcgen05: ws[split][Ca][9][Cb] += sum_pix p[pix][ca] * q[pix+tap][cb] */
+typedef struct {
+  int G, B, H, W;
+  int Ca;          /* channels of p = dL/d(conv output) = Cout, multiple of 64 */
+  int Cb;          /* padded channels of q = conv input: 16 or a multiple of 64 */
+  const void* p;   /* bf16 [G][B][H][W][Ca] */
+  const void* q;   /* bf16 [G][B][H][W][Cb] */
+  float* ws;       /* fp32 [splits][Ca][9][Cb], fabric_b200_conv3x3_wgrad_ws_floats() */
+  int splits;      /* 0 = auto */
+  int wide;        /* 1 = one N=3*Cb-chunk MMA per K step (overlapping N atoms), 0 = three MMAs */
+} fb_wgrad_desc;
+int64_t fabric_b200_conv3x3_wgrad_ws_floats(const fb_wgrad_desc* d);
+int fabric_b200_conv3x3_wgrad_splits(const fb_wgrad_desc* d);
+int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream);
+/* sum the split-K partials and transpose to nn.Conv2d layout: dw [Cout][Cin][3][3] fp32 */
+int fabric_b200_wgrad_reduce(const float* ws, int splits, int Cout, int Cin, int CinPad, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

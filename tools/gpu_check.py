@@ -252,6 +252,222 @@ def group_fwd():
     emit(rec)
 
 
+
+
+# ================================================================================================ training path
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def _case(name, fn):
+    rec = dict(case=name)
+    try:
+        rec.update(fn())
+        rec["ok"] = bool(rec.pop("_ok"))
+    except Exception as e:  # noqa
+        import traceback
+        rec.update(ok=False, error=repr(e)[:300], tb=traceback.format_exc()[-600:])
+    emit(rec)
+
+
+def group_train_units():
+    dev = "cuda"
+    torch.manual_seed(0)
+
+    def bn_fwd():
+        G, B, H, W, cin, C = 2, 3, 20, 12, 64, 128
+        x5 = torch.randn(G, B, H, W, cin, device=dev).bfloat16()
+        w = torch.randn(C, cin, 3, 3, device=dev) / 24
+        bias = torch.randn(C, device=dev)
+        bn = torch.nn.BatchNorm2d(C).to(dev)
+        bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
+        ref_bn = torch.nn.BatchNorm2d(C).to(dev); ref_bn.load_state_dict(bn.state_dict())
+        r = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), C, stats=True)
+        s = ops.bn_finalize(r["stats"], bn, bias, B * H * W, G)
+        a, pl = ops.bn_apply_relu(r["y"], s[0], s[1], pool=True)
+        z = r["y"].float()  # stored conv output (no bias)
+        outs = []
+        for g in range(G):
+            zg = z[g].permute(0, 3, 1, 2) + bias[None, :, None, None]
+            outs.append(torch.relu(ref_bn(zg)))
+        ref = torch.stack(outs).permute(0, 1, 3, 4, 2)
+        e_a = _rel(a.float(), ref)
+        e_p = _rel(pl.float(), F.max_pool2d(a.float().reshape(G * B, H, W, C).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(pl.shape))
+        e_rm = _rel(bn.running_mean, ref_bn.running_mean)
+        e_rv = _rel(bn.running_var, ref_bn.running_var)
+        nbt = int(bn.num_batches_tracked)
+        return dict(e_a=e_a, e_pool=e_p, e_rm=e_rm, e_rv=e_rv, nbt=nbt,
+                    _ok=e_a < 5e-3 and e_p == 0 and e_rm < 1e-4 and e_rv < 1e-4 and nbt == 2)
+    _case("bn_finalize_apply", bn_fwd)
+
+    def losses():
+        from oracle import bidatenet_oracle as O
+        B, H, W = 3, 24, 40
+        logits = torch.randn(B, 2, H, W) * 2
+        labels = (torch.rand(B, H, W) < 0.2).long()
+        out = {}
+        ok = True
+        for kind, fn in (("tversky", lambda l, t: O.tversky_loss(l, t, 0.1, 0.9)), ("dice", O.dice_loss),
+                         ("jaccard", O.jaccard_loss), ("focal", lambda l, t: O.focal_loss(l, t, 2.0)),
+                         ("ce", O.cross_entropy_loss)):
+            for nd, lab in (("3d", labels), ("4d", labels[:, None])):
+                l = logits.clone().requires_grad_(True)
+                v = fn(l, lab); v.backward()
+                loss, dl = ops.seg_loss_fwd_bwd(kind, logits.to(dev), lab.to(dev), 0.1, 0.9, 2.0, 1e-7)
+                ev = abs(float(loss) - float(v)); eg = _rel(dl.cpu(), l.grad)
+                out[f"{kind}_{nd}"] = (ev, eg)
+                ok = ok and ev < 2e-6 and eg < 1e-4
+        return dict(errs=out, _ok=ok)
+    _case("losses", losses)
+
+    def head_bwd():
+        B, H, W, C = 2, 20, 28, 64
+        u = torch.randn(1, B, H, W, C, device=dev).bfloat16()
+        w = (torch.randn(2, C, 1, 1, device=dev) * 0.2).requires_grad_(True)
+        b = torch.randn(2, device=dev).requires_grad_(True)
+        uf = u[0].float().permute(0, 3, 1, 2).requires_grad_(True)
+        dl = torch.randn(B, 2, H, W, device=dev)
+        F.conv2d(uf, w, b).backward(dl)
+        du, dw, db = ops.outconv_bwd(dl, u, w)
+        e = (_rel(du[0].float(), uf.grad.permute(0, 2, 3, 1)), _rel(dw, w.grad), _rel(db, b.grad))
+        return dict(errs=e, _ok=e[0] < 5e-3 and e[1] < 1e-4 and e[2] < 1e-4)
+    _case("outconv_bwd", head_bwd)
+
+    def bn_bwd(quad):
+        G, B, H, W, C = 2, 2, 13, 10, 64
+        z = torch.randn(G, B, H, W, C, device=dev).bfloat16()
+        bn = torch.nn.BatchNorm2d(C).to(dev)
+        bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.3)
+        zf = z.float().requires_grad_(True)
+        gam = bn.weight.detach().clone().requires_grad_(True)
+        bet = bn.bias.detach().clone().requires_grad_(True)
+        # reference forward per date group
+        acts, stats = [], []
+        for g in range(G):
+            x = zf[g].permute(0, 3, 1, 2)
+            m = x.mean((0, 2, 3)); v = x.var((0, 2, 3), unbiased=False)
+            inv = torch.rsqrt(v + 1e-5)
+            stats.append((m.detach(), inv.detach()))
+            acts.append(torch.relu((x - m[None, :, None, None]) * inv[None, :, None, None] * gam[None, :, None, None]
+                                   + bet[None, :, None, None]))
+        mean = torch.stack([s[0] for s in stats]); invstd = torch.stack([s[1] for s in stats])
+        scale = gam.detach()[None] * invstd
+        shift = bet.detach()[None] - mean * scale
+        a5, _ = ops.bn_apply_relu(z, scale.contiguous(), shift.contiguous())
+        # the kernel's activation is bf16; make the reference consume exactly that tensor where it is an input
+        a_ref = [a.permute(0, 2, 3, 1) for a in acts]
+        if quad:
+            # loss = sum(gcat[..., :C] * relu(a0*a1)) + sum(gp * maxpool(a_g))
+            gcat = torch.randn(1, B, H, W, 2 * C, device=dev).bfloat16()
+            gp = torch.randn(G, B, H // 2, W // 2, C, device=dev).bfloat16()
+            prod = torch.relu(a_ref[0] * a_ref[1])
+            loss = (gcat[0, ..., :C].float() * prod).sum()
+            for g in range(G):
+                loss = loss + (gp[g].float().permute(0, 3, 1, 2) * F.max_pool2d(acts[g], 2)).sum()
+            loss.backward()
+            dz, dg, db = ops.bn_relu_bwd(z, a5, gcat, True, gp, scale.contiguous(), shift.contiguous(), mean.contiguous(),
+                                         invstd.contiguous(), gam)
+        else:
+            ga = torch.randn(G, B, H, W, C, device=dev).bfloat16()
+            loss = sum((ga[g].float() * a_ref[g]).sum() for g in range(G))
+            loss.backward()
+            dz, dg, db = ops.bn_relu_bwd(z, None, ga, False, None, scale.contiguous(), shift.contiguous(), mean.contiguous(),
+                                         invstd.contiguous(), gam)
+        e = (_rel(dz.float(), zf.grad), _rel(dg, gam.grad), _rel(db, bet.grad))
+        return dict(errs=e, _ok=e[0] < 1.5e-2 and e[1] < 1e-2 and e[2] < 1e-2)
+    _case("bn_relu_bwd_plain", lambda: bn_bwd(False))
+    _case("bn_relu_bwd_product_pool", lambda: bn_bwd(True))
+
+    def up_bwd():
+        out = {}
+        ok = True
+        for (H, W, h, w) in ((32, 32, 16, 16), (11, 11, 5, 5), (45, 45, 22, 22)):
+            B, Cs, Cl = 2, 64, 128
+            dcat = torch.randn(1, B, H, W, Cs + Cl, device=dev).bfloat16()
+            low = torch.randn(B, Cl, h, w, device=dev, requires_grad=True)
+            x1 = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)
+            dy, dx = H - x1.shape[2], W - x1.shape[3]
+            x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+            (x1 * dcat[0, ..., Cs:].float().permute(0, 3, 1, 2)).sum().backward()
+            dlow = ops.up_input_bwd(dcat, Cs, h, w)
+            e = _rel(dlow[0].float(), low.grad.permute(0, 2, 3, 1))
+            out[f"{H}"] = e
+            ok = ok and e < 5e-3
+        return dict(errs=out, _ok=ok)
+    _case("up_input_bwd", up_bwd)
+
+    def wgrad(G, B, H, W, cin, cout, wide):
+        cp = ops.cpad(cin)
+        x5 = torch.zeros(G, B, H, W, cp, device=dev, dtype=torch.bfloat16)
+        x5[..., :cin] = torch.randn(G, B, H, W, cin, device=dev).bfloat16()
+        dz = torch.randn(G, B, H, W, cout, device=dev).bfloat16()
+        xf = x5[..., :cin].float().reshape(G * B, H, W, cin).permute(0, 3, 1, 2)
+        wt = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
+        (F.conv2d(xf, wt, padding=1) * dz.float().reshape(G * B, H, W, cout).permute(0, 3, 1, 2)).sum().backward()
+        dw = ops.conv3x3_wgrad(dz, x5, cin, wide=wide)
+        e = _rel(dw, wt.grad)
+        return dict(err=e, _ok=e < 2e-3)
+    for wide in (0, 1):
+        _case(f"wgrad_64_64_w{wide}", lambda: wgrad(1, 2, 32, 24, 64, 64, wide))
+        _case(f"wgrad_128_256_w{wide}", lambda: wgrad(2, 3, 20, 12, 128, 256, wide))
+        _case(f"wgrad_stem13_w{wide}", lambda: wgrad(2, 2, 32, 32, 13, 64, wide))
+        _case(f"wgrad_small4_w{wide}", lambda: wgrad(2, 5, 4, 4, 128, 128, wide))
+        _case(f"wgrad_odd45_w{wide}", lambda: wgrad(1, 2, 45, 45, 64, 128, wide))
+
+    def dgrad():
+        G, B, H, W, cin, cout = 2, 2, 20, 12, 128, 64
+        dz = torch.randn(G, B, H, W, cout, device=dev).bfloat16()
+        w = torch.randn(cout, cin, 3, 3, device=dev) / 30
+        x = torch.zeros(G * B, cin, H, W, device=dev, requires_grad=True)
+        (F.conv2d(x, w.bfloat16().float(), padding=1) * dz.float().reshape(G * B, H, W, cout).permute(0, 3, 1, 2)).sum().backward()
+        dx = ops.conv3x3(dz, ops.pack_conv_weight(w, 1), cin)["y"]
+        e = _rel(dx.float().reshape(G * B, H, W, cin).permute(0, 3, 1, 2), x.grad)
+        return dict(err=e, _ok=e < 5e-3)
+    _case("dgrad", dgrad)
+
+
+def group_train_model():
+    from fabric_b200 import BiDateNet
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    golden = torch.load(os.path.join(ROOT, "tests", "golden", "bidatenet_golden.pt"))
+    sd = O.make_state_dict(seed=0)
+
+    def step():
+        model = BiDateNet(13, 2)
+        model.load_state_dict(sd)
+        model = model.cuda().train()
+        x1, x2, labels = golden["c1_x1"].cuda(), golden["c1_x2"].cuda(), golden["c1_labels"].cuda()
+        logits = model(x1, x2)
+        loss = TverskyLoss(alpha=0.1, beta=0.9)(logits, labels)
+        loss.backward()
+        out = dict(logits_rel=_rel(logits.detach().cpu(), golden["c1_logits_train"]),
+                   loss=float(loss), loss_ref=float(golden["c1_loss_train"]))
+        worst = ("", 0.0)
+        errs = {}
+        for k, p in model.named_parameters():
+            ref_n = float(golden["c1_gradnorm/" + k])
+            g = p.grad.detach().cpu()
+            if k.endswith(".0.bias") or k.endswith(".3.bias"):
+                continue
+            en = abs(float(g.norm()) - ref_n) / (ref_n + 1e-30)
+            if ("c1_grad/" + k) in golden:
+                en = max(en, _rel(g, golden["c1_grad/" + k]))
+            errs[k] = en
+            if en > worst[1]:
+                worst = (k, en)
+        out["worst_grad"] = worst
+        out["grad_errs"] = {k: round(v, 4) for k, v in errs.items()}
+        st = model.state_dict()
+        es = max(_rel(st[k[len("c1_newstat/"):]].float().cpu(), v.float()) for k, v in golden.items()
+                 if k.startswith("c1_newstat/") and "num_batches" not in k)
+        out["stats_rel"] = es
+        out["nbt"] = (int(st["inc.conv.conv.1.num_batches_tracked"]), int(st["up1.conv.conv.1.num_batches_tracked"]))
+        out["_ok"] = out["logits_rel"] < 3e-2 and abs(out["loss"] - out["loss_ref"]) < 5e-3 and worst[1] < 0.15 and es < 2e-2
+        return out
+    _case("train_step_c1_vs_reference_golden", step)
+
+
 if __name__ == "__main__":
     for g in sys.argv[1:]:
         globals()["group_" + g]()

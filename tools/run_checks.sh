@@ -18,5 +18,5 @@ for l in sys.stdin:
     except Exception:
         print(l.rstrip()[:300])
 '
-for g in ${GROUPS_OK:-tap halo misc model}; do echo "=== $g"; timeout 300 python tools/gpu_check.py $g 2>&1 | python -c "$fmt_ok" | grep -v " OK$"; done
-for g in ${GROUPS_T:-bench fwd}; do echo "=== $g"; timeout 300 python tools/gpu_check.py $g 2>&1 | python -c "$fmt_t"; done
+for g in ${GROUPS_OK-tap halo misc model}; do echo "=== $g"; timeout 300 python tools/gpu_check.py $g 2>&1 | python -c "$fmt_ok" | grep -v " OK$"; done
+for g in ${GROUPS_T-bench fwd}; do echo "=== $g"; timeout 300 python tools/gpu_check.py $g 2>&1 | python -c "$fmt_t"; done
