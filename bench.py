@@ -199,18 +199,35 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    if args.workload == "train":
-        raise SystemExit("train workload: backward kernels are not built yet (round 1 measures configs[1])")
-
     torch.manual_seed(0)
-    model = BiDateNet(13, 2).to(dev).eval()
+    train = args.workload == "train"
+    model = BiDateNet(13, 2).to(dev)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x1 = torch.randn(PAIRS, 13, SIZE, SIZE, device=dev, generator=g)
     x2 = torch.randn(PAIRS, 13, SIZE, SIZE, device=dev, generator=g)
+    labels = (torch.rand(PAIRS, SIZE, SIZE, device=dev, generator=g) < 0.1).long()
+    if train:
+        from fabric_b200.distributed import DataParallelStep
+        from fabric_b200.metrics import TverskyLoss
+        model.train()
+        criterion = TverskyLoss(alpha=0.1, beta=0.9)                  # metadata.json:42-44
+        optimizer = torch.optim.SGD(model.parameters(), lr=1e-3)     # train.py:55, metadata.json:41
+        dp = DataParallelStep(model)
+        dp.broadcast_parameters(0)
 
-    def step():
-        with torch.no_grad():
-            return model(x1, x2)
+        def step(a=x1, b=x2, lab=labels):                            # train.py:88-95
+            optimizer.zero_grad(set_to_none=True)
+            loss = criterion(model(a, b), lab)
+            loss.backward()
+            dp.sync()                                                 # ONE NCCL all-reduce (no-op for N = 1)
+            optimizer.step()
+            return loss
+    else:
+        model.eval()
+
+        def step(a=x1, b=x2, lab=None):
+            with torch.no_grad():
+                return model(a, b)
 
     def barrier():
         if world > 1:
@@ -258,7 +275,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "conv3x3_umma_kernel (all 18 launches of a step)",
+    roofline = {"bound": "tensor", "kernel": "conv3x3_umma_kernel (fwd + dgrad launches)" + (" + wgrad_umma_kernel" if train else "") + ", all launches of a step",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops_sustained"], "frac_of_burst_peak": achieved / peaks["tflops"],
                 "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
@@ -266,29 +283,44 @@ def main():
                 "algorithmic_gflop_per_step": conv_flops / args.steps / 1e9}
 
     # ---- end to end: host (pinned) -> device -> forward -> logits back to host, through the public API ---------
-    e2e = None
-    if True:
-        hp1 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
-        hp2 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
+    hp1 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
+    hp2 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
+    if train:
+        # reference train.py:83-95 per batch: host batch -> device, step, loss back to the host (.item(), helpers.py:83)
+        hlab = (torch.rand(PAIRS, SIZE, SIZE) < 0.1).long().pin_memory()
+        dx1, dx2, dlab = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(labels)
+
+        def e2e_step():
+            dx1.copy_(hp1, non_blocking=True)
+            dx2.copy_(hp2, non_blocking=True)
+            dlab.copy_(hlab, non_blocking=True)
+            return step(dx1, dx2, dlab).item()
+        h2d = 2 * hp1.numel() * 4 + hlab.numel() * 8
+        d2h = 4
+        api = "model(x1,x2); TverskyLoss(logits, labels); loss.backward(); DataParallelStep.sync(); SGD.step(); loss.item()"
+    else:
         hout = torch.empty(PAIRS, 2, SIZE, SIZE).pin_memory()
         pipe = HostPipeline(model, chunk=16, n_channels=13, size=SIZE, return_logits=True)
-        for _ in range(2):
-            pipe.run(hp1, hp2, hout)
-        barrier()
-        t0 = time.perf_counter()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.e2e_steps):
-            h2d, d2h = pipe.run(hp1, hp2, hout)
-        b.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        tt = torch.tensor([max(a.elapsed_time(b) / 1e3, wall)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": PAIRS * world * args.e2e_steps / float(tt.item()), "unit": "patch-pairs/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
-               "api": "fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, 16-pair sub-batches)"}
+        res = {}
+
+        def e2e_step():
+            res["b"] = pipe.run(hp1, hp2, hout)
+        e2e_step()
+        h2d, d2h = res["b"]
+        api = "fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, 16-pair sub-batches)"
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = {"value": PAIRS * world * args.e2e_steps / float(tt.item()), "unit": "patch-pairs/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": api}
 
     if rank == 0:
         cpu = None
@@ -299,7 +331,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_dict(args.workload, world),
-            "tflops_per_gpu": FWD_GFLOP_PER_PAIR * PAIRS / ms_step,
+            "tflops_per_gpu": (TRAIN_GFLOP_PER_PAIR if train else FWD_GFLOP_PER_PAIR) * PAIRS / ms_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "layers": layers,
         }

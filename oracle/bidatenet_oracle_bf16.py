@@ -1,0 +1,84 @@
+"""Precision-model oracle: the SAME algorithm as ``bidatenet_oracle.py`` (fp32 CPU restatement of the reference),
+with every tensor the CUDA path keeps in HBM as bf16 rounded to bf16 at the point it is stored (conv outputs,
+post-BN/ReLU activations, the concatenated decoder input, packed weights, and the corresponding gradients in the
+backward pass).  All arithmetic stays fp32, exactly as the kernels accumulate.  TEST INFRASTRUCTURE ONLY.
+
+Why it exists: against the fp32 oracle the bf16 path is bounded by bf16 storage error, which for a few quantities is
+large by construction -- the gradients of BatchNorm affine parameters are sums with near-total cancellation (the
+gradient reaching a BN through the following conv+BN sums to ~0 over pixels), so at the tiny CPU-runnable config
+(batch 2, 32x32) bf16 rounding noise is 30-50 % of those sums.  This oracle lets the tests separate "bf16 storage"
+from "kernel bug": the CUDA path must agree with it much more tightly than with the fp32 oracle.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import bidatenet_oracle as O
+
+
+class _Round(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+r = _Round.apply
+
+
+def _bn_train(x, w, b, eps=O.BN_EPS):
+    m = x.mean((0, 2, 3))
+    v = x.var((0, 2, 3), unbiased=False)
+    return (x - m[None, :, None, None]) * torch.rsqrt(v + eps)[None, :, None, None] * w[None, :, None, None] \
+        + b[None, :, None, None]
+
+
+def double_conv(x, P, pre, training):
+    """models/unet_parts.py:8-23 with bf16 storage points"""
+    w1, w2 = r(P[pre + ".0.weight"]), r(P[pre + ".3.weight"])
+    if training:
+        z1 = r(F.conv2d(x, w1, None, padding=1))          # conv bias cancels against the batch mean
+        a1 = r(F.relu(_bn_train(z1, P[pre + ".1.weight"], P[pre + ".1.bias"])))
+        z2 = r(F.conv2d(a1, w2, None, padding=1))
+        return r(F.relu(_bn_train(z2, P[pre + ".4.weight"], P[pre + ".4.bias"])))
+    out = x
+    for ci, bi, w in ((0, 1, w1), (3, 4, w2)):
+        scale = P[f"{pre}.{bi}.weight"] / torch.sqrt(P[f"{pre}.{bi}.running_var"] + O.BN_EPS)
+        shift = (P[f"{pre}.{ci}.bias"] - P[f"{pre}.{bi}.running_mean"]) * scale + P[f"{pre}.{bi}.bias"]
+        out = r(F.relu(F.conv2d(out, w, None, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]))
+    return out
+
+
+def forward(x_d1, x_d2, P, training=False):
+    """models/bidate_model.py:22-40 with bf16 storage points"""
+    def enc(x):
+        outs = [double_conv(r(x), P, "inc.conv.conv", training)]
+        for n in ("down1", "down2", "down3", "down4"):
+            outs.append(double_conv(F.max_pool2d(outs[-1], 2), P, f"{n}.mpconv.1.conv", training))
+        return outs
+
+    def up(x1, x2, n):
+        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return double_conv(r(torch.cat([x2, x1], 1)), P, f"{n}.conv.conv", training)
+
+    e1, e2 = enc(x_d1), enc(x_d2)
+    f = [torch.relu(a * b) for a, b in zip(e1, e2)]
+    x = up(f[4], f[3], "up1")
+    x = up(x, f[2], "up2")
+    x = up(x, f[1], "up3")
+    x = up(x, f[0], "up4")
+    return F.conv2d(x, P["outc.conv.weight"], P["outc.conv.bias"])
+
+
+def train_step(x_d1, x_d2, labels, sd, criterion):
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running_" not in k}
+    logits = forward(x_d1, x_d2, P, training=True)
+    loss = criterion(logits, labels)
+    grads = torch.autograd.grad(loss, list(P.values()), allow_unused=True)
+    return loss.detach(), logits.detach(), {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(P, grads)}

@@ -1,0 +1,268 @@
+"""GPU parity tests of the TRAINING path (run with -m gpu on a B200): loss kernels, BatchNorm batch statistics,
+backward kernels, and one full training step against (a) the golden numbers the unmodified reference produced and
+(b) the bf16 precision-model oracle.
+
+Tolerances: kernels keep activations / activation gradients in bf16 and accumulate in fp32.
+  * losses (fp32 in, fp32 out): |dloss| <= 2e-6, gradient rel-L2 <= 1e-4 vs the oracle;
+  * one bf16-stored tensor produced from exact inputs: rel-L2 <= 5e-3; weight gradient of one conv from exact
+    bf16 operands (fp32 accumulate, fp32 out): rel-L2 <= 1e-4;
+  * whole training step at config 1 (batch 2, 13x32x32): train-mode logits rel-L2 <= 6e-2 vs the fp32 reference
+    (measured 4.1e-2; the precision-model oracle itself sits at 4.0e-2), loss |d| <= 2e-3, conv weight gradients
+    rel-L2 <= 0.12 vs fp32 reference, and every gradient incl. the cancellation-dominated BatchNorm gamma/beta
+    gradients rel-L2 <= 0.15 vs the precision-model oracle (see oracle/bidatenet_oracle_bf16.py for why those are
+    30-50 % off the fp32 reference at this batch size for ANY bf16-storage implementation).
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fabric_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("kind", ["tversky", "dice", "jaccard", "focal", "ce"])
+@pytest.mark.parametrize("nd", [3, 4])
+def test_losses_match_oracle(cuda, kind, nd):
+    from fabric_b200 import ops
+    from oracle import bidatenet_oracle as O
+    torch.manual_seed(1)
+    B, H, W = 3, 24, 40
+    logits = torch.randn(B, 2, H, W) * 2
+    labels = (torch.rand(B, H, W) < 0.2).long()
+    lab = labels if nd == 3 else labels[:, None]
+    fn = {"tversky": lambda l, t: O.tversky_loss(l, t, 0.1, 0.9), "dice": O.dice_loss, "jaccard": O.jaccard_loss,
+          "focal": lambda l, t: O.focal_loss(l, t, 2.0), "ce": O.cross_entropy_loss}[kind]
+    l = logits.clone().requires_grad_(True)
+    v = fn(l, lab)
+    v.backward()
+    loss, dl = ops.seg_loss_fwd_bwd(kind, logits.to(cuda), lab.to(cuda), 0.1, 0.9, 2.0, 1e-7)
+    assert abs(float(loss) - float(v.detach())) <= 2e-6
+    assert rel(dl.cpu(), l.grad) <= 1e-4
+
+
+def test_losses_match_reference_golden(cuda, golden):
+    """loss values and dL/dlogits the unmodified reference produced on config-1 logits, 3-D and 4-D labels"""
+    from fabric_b200 import metrics
+    logits, labels = golden["c1_logits_eval"].to(cuda), golden["c1_labels"].to(cuda)
+    crit = {"dice": metrics.dice_loss, "jaccard": metrics.jaccard_loss, "tversky": metrics.TverskyLoss(alpha=0.1, beta=0.9),
+            "focal": metrics.FocalLoss(gamma=2.0)}
+    for name, fn in crit.items():
+        for nd, lab in (("3d", labels), ("4d", labels[:, None])):
+            l = logits.clone().requires_grad_(True)
+            v = fn(l, lab)
+            v.backward()
+            assert abs(v.item() - float(golden[f"c1_loss_{name}_{nd}"])) <= 2e-6, (name, nd)
+            assert rel(l.grad.cpu(), golden[f"c1_dlogits_{name}_{nd}"]) <= 1e-4, (name, nd)
+
+
+def test_bn_train_forward_matches_torch(cuda):
+    """conv epilogue moments -> bn_finalize -> bn_apply(+pool) vs nn.BatchNorm2d(train) per date group
+    (reference unet_parts.py:14-15,40), including running statistics and num_batches_tracked"""
+    from fabric_b200 import ops
+    torch.manual_seed(2)
+    G, B, H, W, cin, C = 2, 3, 20, 12, 64, 128
+    x5 = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
+    w = torch.randn(C, cin, 3, 3, device=cuda) / 24
+    bias = torch.randn(C, device=cuda)
+    bn = torch.nn.BatchNorm2d(C).to(cuda)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    ref_bn = torch.nn.BatchNorm2d(C).to(cuda)
+    ref_bn.load_state_dict(bn.state_dict())
+    r = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), C, stats=True)
+    s = ops.bn_finalize(r["stats"], bn, bias, B * H * W, G)
+    a, pl = ops.bn_apply_relu(r["y"], s[0], s[1], pool=True)
+    z = r["y"].float()
+    ref = torch.stack([torch.relu(ref_bn(z[g].permute(0, 3, 1, 2) + bias[None, :, None, None])) for g in range(G)])
+    assert rel(a.float(), ref.permute(0, 1, 3, 4, 2)) <= 5e-3
+    pooled_ref = F.max_pool2d(a.float().reshape(G * B, H, W, C).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(pl.float().reshape(pooled_ref.shape), pooled_ref)
+    assert rel(bn.running_mean, ref_bn.running_mean) <= 1e-5 and rel(bn.running_var, ref_bn.running_var) <= 1e-5
+    assert int(bn.num_batches_tracked) == 2 == int(ref_bn.num_batches_tracked)
+
+
+@pytest.mark.parametrize("G,B,H,W,cin,cout,wide", [
+    (1, 2, 32, 24, 64, 64, 0), (1, 2, 32, 24, 64, 64, 1), (2, 3, 20, 12, 128, 256, 1), (2, 2, 32, 32, 13, 64, 1),
+    (2, 2, 32, 32, 13, 64, 0), (2, 5, 4, 4, 128, 128, 1), (1, 2, 45, 45, 64, 128, 1), (2, 3, 2, 2, 64, 64, 1)])
+def test_wgrad_matches_torch(cuda, G, B, H, W, cin, cout, wide):
+    from fabric_b200 import ops
+    torch.manual_seed(3)
+    cp = ops.cpad(cin)
+    x5 = torch.zeros(G, B, H, W, cp, device=cuda, dtype=torch.bfloat16)
+    x5[..., :cin] = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
+    dz = torch.randn(G, B, H, W, cout, device=cuda).bfloat16()
+    xf = x5[..., :cin].float().reshape(G * B, H, W, cin).permute(0, 3, 1, 2)
+    wt = torch.zeros(cout, cin, 3, 3, device=cuda, requires_grad=True)
+    (F.conv2d(xf, wt, padding=1) * dz.float().reshape(G * B, H, W, cout).permute(0, 3, 1, 2)).sum().backward()
+    dw = ops.conv3x3_wgrad(dz, x5, cin, wide=wide)
+    assert dw.shape == wt.shape
+    assert rel(dw, wt.grad) <= 1e-4
+
+
+def test_dgrad_matches_torch(cuda):
+    from fabric_b200 import ops
+    torch.manual_seed(4)
+    G, B, H, W, cin, cout = 2, 2, 20, 12, 128, 64
+    dz = torch.randn(G, B, H, W, cout, device=cuda).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, device=cuda) / 30
+    x = torch.zeros(G * B, cin, H, W, device=cuda, requires_grad=True)
+    (F.conv2d(x, w.bfloat16().float(), padding=1) * dz.float().reshape(G * B, H, W, cout).permute(0, 3, 1, 2)).sum().backward()
+    dx = ops.conv3x3(dz, ops.pack_conv_weight(w, 1), cin)["y"]
+    assert rel(dx.float().reshape(G * B, H, W, cin).permute(0, 3, 1, 2), x.grad) <= 5e-3
+
+
+@pytest.mark.parametrize("H,W,h,w", [(32, 32, 16, 16), (11, 11, 5, 5), (45, 45, 22, 22)])
+def test_up_input_bwd_is_adjoint_of_bilinear_pad(cuda, H, W, h, w):
+    from fabric_b200 import ops
+    torch.manual_seed(5)
+    B, Cs, Cl = 2, 64, 128
+    dcat = torch.randn(1, B, H, W, Cs + Cl, device=cuda).bfloat16()
+    low = torch.randn(B, Cl, h, w, device=cuda, requires_grad=True)
+    x1 = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = H - x1.shape[2], W - x1.shape[3]
+    x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    (x1 * dcat[0, ..., Cs:].float().permute(0, 3, 1, 2)).sum().backward()
+    dlow = ops.up_input_bwd(dcat, Cs, h, w)
+    assert rel(dlow[0].float(), low.grad.permute(0, 2, 3, 1)) <= 5e-3
+
+
+def _bn_bwd_case(cuda, quad):
+    from fabric_b200 import ops
+    torch.manual_seed(6)
+    G, B, H, W, C = 2, 2, 13, 10, 64
+    z = torch.randn(G, B, H, W, C, device=cuda).bfloat16()
+    gam = torch.empty(C, device=cuda).uniform_(0.5, 1.5).requires_grad_(True)
+    bet = (0.3 * torch.randn(C, device=cuda)).requires_grad_(True)
+    zf = z.float().requires_grad_(True)
+    acts, mean, invstd = [], [], []
+    for g in range(G):
+        x = zf[g].permute(0, 3, 1, 2)
+        m, v = x.mean((0, 2, 3)), x.var((0, 2, 3), unbiased=False)
+        inv = torch.rsqrt(v + 1e-5)
+        mean.append(m.detach()), invstd.append(inv.detach())
+        acts.append(torch.relu((x - m[None, :, None, None]) * inv[None, :, None, None] * gam[None, :, None, None]
+                               + bet[None, :, None, None]))
+    mean, invstd = torch.stack(mean), torch.stack(invstd)
+    scale = (gam.detach()[None] * invstd).contiguous()
+    shift = (bet.detach()[None] - mean * scale).contiguous()
+    a5, _ = ops.bn_apply_relu(z, scale, shift)
+    a_ref = [a.permute(0, 2, 3, 1) for a in acts]
+    if quad:   # product fusion relu(d2*d1) (bidate_model.py:35-38) + MaxPool2d (unet_parts.py:40) adjoints
+        gcat = torch.randn(1, B, H, W, 2 * C, device=cuda).bfloat16()
+        gp = torch.randn(G, B, H // 2, W // 2, C, device=cuda).bfloat16()
+        loss = (gcat[0, ..., :C].float() * torch.relu(a_ref[0] * a_ref[1])).sum()
+        for g in range(G):
+            loss = loss + (gp[g].float().permute(0, 3, 1, 2) * F.max_pool2d(acts[g], 2)).sum()
+        loss.backward()
+        dz, dg, db = ops.bn_relu_bwd(z, a5, gcat, True, gp, scale, shift, mean.contiguous(), invstd.contiguous(), gam)
+    else:
+        ga = torch.randn(G, B, H, W, C, device=cuda).bfloat16()
+        sum((ga[g].float() * a_ref[g]).sum() for g in range(G)).backward()
+        dz, dg, db = ops.bn_relu_bwd(z, None, ga, False, None, scale, shift, mean.contiguous(), invstd.contiguous(), gam)
+    return rel(dz.float(), zf.grad), rel(dg, gam.grad), rel(db, bet.grad)
+
+
+def test_bn_relu_bwd_plain(cuda):
+    e = _bn_bwd_case(cuda, False)
+    assert e[0] <= 5e-3 and e[1] <= 1e-4 and e[2] <= 1e-4
+
+
+def test_bn_relu_bwd_with_product_and_pool_adjoints(cuda):
+    e = _bn_bwd_case(cuda, True)      # the other date's activation enters as a bf16 tensor: looser
+    assert e[0] <= 1.5e-2 and e[1] <= 5e-3 and e[2] <= 5e-3
+
+
+def test_outconv_bwd_matches_torch(cuda):
+    from fabric_b200 import ops
+    torch.manual_seed(7)
+    B, H, W, C = 2, 20, 28, 64
+    u = torch.randn(1, B, H, W, C, device=cuda).bfloat16()
+    w = (torch.randn(2, C, 1, 1, device=cuda) * 0.2).requires_grad_(True)
+    b = torch.randn(2, device=cuda).requires_grad_(True)
+    uf = u[0].float().permute(0, 3, 1, 2).requires_grad_(True)
+    dl = torch.randn(B, 2, H, W, device=cuda)
+    F.conv2d(uf, w, b).backward(dl)
+    du, dw, db = ops.outconv_bwd(dl, u, w)
+    assert rel(du[0].float(), uf.grad.permute(0, 2, 3, 1)) <= 5e-3
+    assert rel(dw, w.grad) <= 1e-4 and rel(db, b.grad) <= 1e-4
+
+
+def test_training_step_config1(cuda, golden):
+    """BASELINE configs[0]: B=2, 13x32x32, forward(train) + Tversky(0.1,0.9) + backward, through the reference-facing
+    API (model(x1,x2); criterion(logits, labels); loss.backward()) -- reference train.py:88-94."""
+    from fabric_b200 import BiDateNet
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    from oracle import bidatenet_oracle_bf16 as Q
+    sd = O.make_state_dict(seed=0)
+    model = BiDateNet(13, 2)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train()
+    x1, x2, labels = golden["c1_x1"], golden["c1_x2"], golden["c1_labels"]
+    logits = model(x1.to(cuda), x2.to(cuda))
+    loss = TverskyLoss(alpha=0.1, beta=0.9)(logits, labels.to(cuda))
+    loss.backward()
+    # (a) against what the unmodified reference produced
+    assert rel(logits.detach().cpu(), golden["c1_logits_train"]) <= 6e-2
+    assert abs(loss.item() - float(golden["c1_loss_train"])) <= 2e-3
+    st = model.state_dict()
+    for k, v in golden.items():
+        if k.startswith("c1_newstat/"):
+            name = k[len("c1_newstat/"):]
+            if "num_batches" in name:
+                assert int(st[name]) == int(v), name         # +2 per step in the encoder, +1 in the decoder
+            else:
+                assert rel(st[name].float().cpu(), v.float()) <= 2e-2, name
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    for k, g in grads.items():
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            assert float(g.abs().max()) == 0.0                # conv bias under train-mode BN: true gradient is zero
+        elif g.dim() == 4:
+            n_ref = float(golden["c1_gradnorm/" + k])
+            assert abs(float(g.norm()) - n_ref) <= 0.12 * n_ref, k
+    assert rel(grads["outc.conv.weight"], golden["c1_grad/outc.conv.weight"]) <= 2e-2
+    # (b) against the bf16 precision-model oracle: every gradient, including BatchNorm gamma/beta
+    _, logits_q, grads_q = Q.train_step(x1, x2, labels, sd, lambda l, t: O.tversky_loss(l, t, 0.1, 0.9))
+    assert rel(logits.detach().cpu(), logits_q) <= 2e-2
+    worst = max((rel(grads[k], grads_q[k]), k) for k in grads if not (k.endswith(".0.bias") or k.endswith(".3.bias")))
+    assert worst[0] <= 0.15, worst
+
+
+def test_train_then_eval_uses_updated_running_stats(cuda):
+    """the eval-mode BN fold cache must see running statistics written by the training kernels"""
+    from fabric_b200 import BiDateNet
+    from fabric_b200.metrics import dice_loss
+    from oracle import bidatenet_oracle as O
+    model = BiDateNet(13, 2)
+    model.load_state_dict(O.make_state_dict(seed=0))
+    model = model.to(cuda)
+    x1, x2, labels = O.make_inputs(2, 32, seed=9)
+    x1, x2, labels = x1.to(cuda), x2.to(cuda), labels.to(cuda)
+    model.eval()
+    with torch.no_grad():
+        before = model(x1, x2).clone()
+    model.train()
+    dice_loss(model(x1, x2), labels).backward()
+    model.eval()
+    with torch.no_grad():
+        after = model(x1, x2)
+    assert not torch.equal(before, after)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ref = O.bidatenet_forward(x1.cpu(), x2.cpu(), sd, training=False)
+    assert rel(after.cpu(), ref) <= 1e-2

@@ -80,3 +80,25 @@ def test_tiler_roundtrip():
         # reassembling channel 0 of the patches gives back channel 0 of the scene (later writes win)
         img = O.get_bands(patches[..., 0], hs, ws, lc, lr, hh, ww, p)
         assert np.array_equal(img.astype(np.float32), bands[..., 0])
+
+
+def test_bf16_precision_model_oracle_brackets_the_reference(golden):
+    """oracle/bidatenet_oracle_bf16.py = same algorithm with bf16 storage points; it must stay within the tolerances
+    the GPU tests state for a bf16 implementation (so those tolerances are about precision, not slack)."""
+    from oracle import bidatenet_oracle_bf16 as Q
+    sd = _sd(golden)
+    with torch.no_grad():
+        out = Q.forward(golden["c1_x1"], golden["c1_x2"], sd, training=False)
+    ref = golden["c1_logits_eval"]
+    assert ((out - ref).norm() / ref.norm()) < 1e-2
+    loss, logits, grads = Q.train_step(golden["c1_x1"], golden["c1_x2"], golden["c1_labels"], sd,
+                                       lambda l, t: O.tversky_loss(l, t, 0.1, 0.9))
+    reft = golden["c1_logits_train"]
+    assert ((logits - reft).norm() / reft.norm()) < 6e-2
+    assert abs(float(loss) - float(golden["c1_loss_train"])) < 2e-3
+    # conv weight gradients survive bf16 storage; BatchNorm gamma/beta gradients (cancellation) do not at batch 2
+    k = "inc.conv.conv.3.weight"
+    assert abs(float(grads[k].norm()) - float(golden["c1_gradnorm/" + k])) < 0.05 * float(golden["c1_gradnorm/" + k])
+    kb = "down3.mpconv.1.conv.1.bias"
+    e = float((grads[kb] - golden["c1_grad/" + kb]).norm() / golden["c1_grad/" + kb].norm())
+    assert 0.05 < e < 1.0
