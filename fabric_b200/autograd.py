@@ -13,6 +13,9 @@ import torch
 
 from . import ops
 
+KEEP_SAVED = False   # tests: keep the stored forward tensors of the last training forward in LAST_SAVED
+LAST_SAVED = None
+
 
 def _dc_forward(dc, x5, pool):
     """double_conv in training mode.  Returns (a2, pooled, saved)."""
@@ -71,6 +74,9 @@ class _BiDateNetTrain(torch.autograd.Function):
         u4, _, sv["up4"] = _dc_forward(model.up4.conv, cat4, False)
         logits = ops.outconv(u4, model.outc.conv.weight, model.outc.conv.bias)   # :39
         ctx.model, ctx.sv, ctx.params = model, sv, params
+        if KEEP_SAVED:
+            global LAST_SAVED
+            LAST_SAVED = sv
         return logits
 
     @staticmethod

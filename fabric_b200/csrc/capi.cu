@@ -109,23 +109,28 @@ int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB
 
 // ------------------------------------------------------------------------------------------------ small kernels
 
-// NCHW fp32 -> NHWC bf16 (channel padded).  One block = one image row segment of 64 pixels.
-__global__ void pack_nchw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int Cpad, int H,
-                                 int W) {
-  extern __shared__ float tile[];  // [Cpad][65]
-  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 64;
-  const int nx = min(64, W - x0);
-  for (int i = threadIdx.x; i < Cpad * 64; i += blockDim.x) {
-    const int c = i / 64, x = i % 64;
-    float v = 0.f;
-    if (c < C && x < nx) v = src[(((size_t)b * C + c) * H + y) * W + x0 + x];
-    tile[c * 65 + x] = v;
+// NCHW fp32 -> NHWC bf16 (channel padded).  One block = PX pixels of one image row: coalesced per-channel row reads
+// into smem, then 16-byte NHWC writes.  PX = 256 for the 13-band input, 32 for wide tensors (standalone block calls).
+__global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        int C, int Cpad, int H, int W, int PX) {
+  extern __shared__ float tile[];  // [C][PX + 1]
+  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * PX;
+  const int nx = min(PX, W - x0);
+  const int P1 = PX + 1;
+  const float* in = src + ((size_t)b * C * H + y) * W + x0;
+  for (int i = threadIdx.x; i < C * PX; i += blockDim.x) {
+    const int c = i / PX, x = i % PX;
+    if (x < nx) tile[c * P1 + x] = __ldg(in + (size_t)c * H * W + x);
   }
   __syncthreads();
-  __nv_bfloat16* out = dst + (((size_t)b * H + y) * W + x0) * Cpad;
-  for (int i = threadIdx.x; i < nx * Cpad / 2; i += blockDim.x) {
-    const int x = (2 * i) / Cpad, c = (2 * i) % Cpad;
-    reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(tile[c * 65 + x], tile[(c + 1) * 65 + x]);
+  uint4* out = reinterpret_cast<uint4*>(dst + (((size_t)b * H + y) * W + x0) * Cpad);
+  const int C8 = Cpad / 8;
+  for (int i = threadIdx.x; i < nx * C8; i += blockDim.x) {
+    const int x = i / C8, c0 = (i % C8) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? tile[(c0 + j) * P1 + x] : 0.f;
+    out[i] = fb::pack8(f);
   }
 }
 
@@ -168,34 +173,33 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
   shift[c] = ((bias ? bias[c] : 0.f) - rm[c]) * s + beta[c];
 }
 
-// decoder input: [skip_d1 * skip_d2 | bilinear x2 (align_corners) of low, zero padded]; one thread = 8 channels
-__global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ low, uint4* __restrict__ out,
-                                      int B, int H, int W, int Cs, int h, int w, int Cl, int low_groups) {
-  const int Ct8 = (Cs + Cl) / 8, Cs8 = Cs / 8, Cl8 = Cl / 8;
-  const size_t total = (size_t)B * H * W * Ct8;
-  const size_t skip_g = (size_t)B * H * W * Cs8;  // one date group of skip, in uint4
-  const size_t low_g = (size_t)B * h * w * Cl8;
+// decoder input: [skip_d1 * skip_d2 | bilinear x2 (align_corners) of low, zero padded]; one thread = 8 channels.
+// 32-bit index math (sizes are checked on the host).
+__global__ void __launch_bounds__(256, 4)
+build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ low, uint4* __restrict__ out, int B, int H,
+                      int W, int Cs, int h, int w, int Cl, int low_groups) {
+  const uint32_t Ct8 = (Cs + Cl) >> 3, Cs8 = Cs >> 3, Cl8 = Cl >> 3;
+  const uint32_t npix = (uint32_t)B * H * W;
+  const uint32_t total = npix * Ct8;
+  const uint32_t skip_g = npix * Cs8;  // one date group of skip, in uint4
+  const uint32_t low_g = (uint32_t)B * h * w * Cl8;
   const int padT = (H - 2 * h) / 2, padL = (W - 2 * w) / 2;
   const float sy = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   const float sx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = i % Ct8;
-    size_t pix = i / Ct8;
-    const int x = pix % W;
-    pix /= W;
-    const int y = pix % H;
-    const int b = pix / H;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t c8 = i % Ct8, pix = i / Ct8;
     float r[8];
     if (c8 < Cs8) {
-      const size_t o = (((size_t)b * H + y) * W + x) * Cs8 + c8;
+      const uint32_t o = pix * Cs8 + c8;
       float a[8], c[8];
-      fb::unpack8(skip[o], a);
-      fb::unpack8(skip[o + skip_g], c);
+      fb::unpack8(__ldg(skip + o), a);
+      fb::unpack8(__ldg(skip + o + skip_g), c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = fmaxf(a[j] * c[j], 0.f);
     } else {
-      const int cl = c8 - Cs8;
-      const int uy = y - padT, ux = x - padL;
+      const uint32_t cl = c8 - Cs8;
+      const uint32_t x = pix % W, t = pix / W, y = t % H, b = t / H;
+      const int uy = (int)y - padT, ux = (int)x - padL;
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = 0.f;
       if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
@@ -205,19 +209,25 @@ __global__ void build_up_input_kernel(const uint4* __restrict__ skip, const uint
         const float ly = fy - y0, lx = fx - x0;
         const float wgt[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
         const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
+        uint4 v0[4], v1[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const size_t o = (((size_t)b * h + ys[t]) * w + xs[t]) * Cl8 + cl;
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t o = ((b * h + ys[k]) * w + xs[k]) * Cl8 + cl;
+          v0[k] = __ldg(low + o);
+          if (low_groups == 2) v1[k] = __ldg(low + o + low_g);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
           float a[8];
-          fb::unpack8(low[o], a);
+          fb::unpack8(v0[k], a);
           if (low_groups == 2) {
             float c[8];
-            fb::unpack8(low[o + low_g], c);
+            fb::unpack8(v1[k], c);
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * c[j], 0.f);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaf(wgt[t], a[j], r[j]);
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(wgt[k], a[j], r[j]);
         }
       }
     }
@@ -274,9 +284,12 @@ int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, i
   if (!src || !dst) return fail(FB_ERR_ARG, "null pointer");
   if (C < 1 || Cpad < C || Cpad % 8 || B < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return fail(FB_ERR_SHAPE, "bad shape");
   if (!aligned16(dst)) return fail(FB_ERR_ALIGN, "dst must be 16-byte aligned");
-  dim3 grid((W + 63) / 64, H, B);
-  pack_nchw_kernel<<<grid, 256, Cpad * 65 * sizeof(float), (cudaStream_t)stream>>>(
-      src, reinterpret_cast<__nv_bfloat16*>(dst), C, Cpad, H, W);
+  const int PX = C <= 32 ? 256 : 32;
+  const size_t smem = (size_t)C * (PX + 1) * sizeof(float);
+  if (smem > (size_t)di.smem_optin) return fail(FB_ERR_SHAPE, "too many channels for the pack kernel");
+  if (smem > 48 * 1024) FB_CUDA(cudaFuncSetAttribute(pack_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((W + PX - 1) / PX, H, B);
+  pack_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, Cpad, H, W, PX);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -378,6 +391,7 @@ int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int
   if (rc) return rc;
   if (!skip || !low || !out) return fail(FB_ERR_ARG, "null pointer");
   if (Cs % 8 || Cl % 8 || 2 * h > H || 2 * w > W || (low_groups != 1 && low_groups != 2)) return fail(FB_ERR_SHAPE, "bad shape");
+  if ((double)B * H * W * (Cs + Cl) / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   if (!aligned16(skip) || !aligned16(low) || !aligned16(out)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
   const size_t n = (size_t)B * H * W * (Cs + Cl) / 8;
   build_up_input_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(

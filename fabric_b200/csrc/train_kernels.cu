@@ -10,6 +10,11 @@ using fb::unpack8;
 
 namespace {
 
+__device__ __forceinline__ void ld8f(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+
 // ================================================================================================ BN forward
 // reference models/unet_parts.py:14,17 (nn.BatchNorm2d in training mode), per date group.
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid, int n_tile, int C, int G, double count,
@@ -17,72 +22,86 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid, in
                                    const float* __restrict__ beta, float* running_mean, float* running_var,
                                    long long* nbt, float momentum, float eps, float* scale, float* shift, float* mean,
                                    float* invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the CTAs' partials
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   const int ntiles = C / n_tile, nt = c / n_tile, lc = c % n_tile;
   float rm = running_mean[c], rv = running_var[c];
   const float b = conv_bias ? conv_bias[c] : 0.f;
   for (int g = 0; g < G; ++g) {  // date 1 first, then date 2: the order in which the reference calls the encoder
     double s1 = 0.0, s2 = 0.0;
-    for (int cta = nt; cta < grid; cta += ntiles) {
-      const float* p = stats + (((size_t)cta * 2 + g) * n_tile + lc) * 2;
-      s1 += p[0];
-      s2 += p[1];
+    for (int cta = nt + lane * ntiles; cta < grid; cta += 32 * ntiles) {
+      const float2 v = *reinterpret_cast<const float2*>(stats + (((size_t)cta * 2 + g) * n_tile + lc) * 2);
+      s1 += v.x;
+      s2 += v.y;
+    }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     const double m = s1 / count;
     double var = s2 / count - m * m;
     if (var < 0.0) var = 0.0;
     const float inv = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = gamma[c] * inv;
-    scale[g * C + c] = sc;
-    shift[g * C + c] = beta[c] - (float)m * sc;  // the conv bias cancels against the batch mean
-    mean[g * C + c] = (float)m;
-    invstd[g * C + c] = inv;
+    if (lane == 0) {
+      scale[g * C + c] = sc;
+      shift[g * C + c] = beta[c] - (float)m * sc;  // the conv bias cancels against the batch mean
+      mean[g * C + c] = (float)m;
+      invstd[g * C + c] = inv;
+    }
     rm = (1.f - momentum) * rm + momentum * ((float)m + b);
     rv = (1.f - momentum) * rv + momentum * (float)(var * (count / (count > 1.0 ? count - 1.0 : 1.0)));
   }
-  running_mean[c] = rm;
-  running_var[c] = rv;
-  if (c == 0 && nbt) *nbt += G;
+  if (lane == 0) {
+    running_mean[c] = rm;
+    running_var[c] = rv;
+    if (c == 0 && nbt) *nbt += G;
+  }
 }
 
-// a = relu(z * scale_g + shift_g) (+ 2x2 max pool).  One thread = 8 channels of one 2x2 pixel quad.
-__global__ void bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                                uint4* __restrict__ a, uint4* __restrict__ pool, int G, int B, int H, int W, int C) {
-  const int C8 = C / 8, Hq = (H + 1) / 2, Wq = (W + 1) / 2, Hp = H / 2, Wp = W / 2;
-  const size_t total = (size_t)G * B * Hq * Wq * C8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = i % C8;
-    size_t q = i / C8;
-    const int qx = q % Wq;
+// a = relu(z * scale_g + shift_g) (+ 2x2 max pool).  One thread = 8 channels of one 2x2 pixel quad; 32-bit indexing.
+__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, uint4* __restrict__ a,
+                                                          uint4* __restrict__ pool, int G, int B, int H, int W, int C) {
+  const uint32_t C8 = C >> 3, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+  const uint32_t total = (uint32_t)G * B * Hq * Wq * C8;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t c8 = i % C8;
+    uint32_t q = i / C8;
+    const uint32_t qx = q % Wq;
     q /= Wq;
-    const int qy = q % Hq;
-    q /= Hq;
-    const int b = q % B;
-    const int g = q / B;
+    const uint32_t qy = q % Hq;
+    q /= Hq;  // = g * B + b
+    const uint32_t g = q >= (uint32_t)B ? 1u : 0u;
     float sc[8], sh[8], m[8];
+    ld8f(scale + g * C + c8 * 8, sc);
+    ld8f(shift + g * C + c8 * 8, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[g * C + c8 * 8 + j];
-      sh[j] = shift[g * C + c8 * 8 + j];
-      m[j] = 0.f;  // post-ReLU values are >= 0
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;  // post-ReLU values are >= 0
+    uint4 zin[4];
+    bool ok[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+      ok[d] = y < (uint32_t)H && x < (uint32_t)W;
+      if (ok[d]) zin[d] = __ldg(z + (size_t)((q * H + y) * W + x) * C8 + c8);
     }
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
-      const int y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-      if (y < H && x < W) {
-        const size_t o = ((((size_t)g * B + b) * H + y) * W + x) * C8 + c8;
-        float f[8];
-        unpack8(z[o], f);
+      if (!ok[d]) continue;
+      const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+      float f[8];
+      unpack8(zin[d], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-          m[j] = fmaxf(m[j], f[j]);
-        }
-        a[o] = pack8(f);
+      for (int j = 0; j < 8; ++j) {
+        f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        m[j] = fmaxf(m[j], f[j]);
       }
+      a[(size_t)((q * H + y) * W + x) * C8 + c8] = pack8(f);
     }
-    if (pool && qy < Hp && qx < Wp) pool[((((size_t)g * B + b) * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
+    if (pool && qy < Hp && qx < Wp) pool[(size_t)((q * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
   }
 }
 
@@ -302,90 +321,109 @@ struct BnBwd {
   int G, B, H, W, C;
 };
 
-// dy for the 8 channels c8 of the 2x2 quad (qy,qx) of image b in group g.  `av` = own activations of the quad (only if
-// needed), returns validity per pixel.
-__device__ __forceinline__ void bn_bwd_dy_quad(const BnBwd& p, int g, int b, int qy, int qx, int c8, float (&dy)[4][8],
-                                               float (&zf)[4][8], bool (&valid)[4]) {
-  const int C8 = p.C / 8;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = p.scale[g * p.C + c8 * 8 + j];
-    sh[j] = p.shift[g * p.C + c8 * 8 + j];
+// dy for the 8 channels c8 of pixel `pix` (index inside one date group: (b*H + y)*W + x) of date group g.
+// Split in two phases so that callers can issue the loads of several pixels before consuming any of them
+// (memory-level parallelism: with one pixel per iteration these kernels sat at 2-2.7 TB/s).
+// All index math is 32-bit (the host checks sizes): 64-bit div/mod per element made the first version ALU-bound.
+struct BnBwdRaw {
+  uint4 z, ga, ao;
+};
+
+__device__ __forceinline__ void bn_bwd_load(const BnBwd& p, uint32_t g, uint32_t pix, uint32_t c8, uint32_t npix, BnBwdRaw& r) {
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t gpix = g * npix + pix;
+  r.z = __ldg(p.z + (size_t)gpix * C8 + c8);
+  if (p.ga) {
+    r.ga = __ldg(p.ga + (size_t)(p.ga_groups == 1 ? pix : gpix) * p.ga_c8 + c8);
+    if (p.mul_other) r.ao = __ldg(p.a + (size_t)((1 - g) * npix + pix) * C8 + c8);
   }
-  float av[4][8];
-  const bool need_a = p.gp != nullptr;
+}
+
+__device__ __forceinline__ void bn_bwd_finish(const BnBwd& p, uint32_t g, uint32_t pix, uint32_t c8, uint32_t npix,
+                                              const BnBwdRaw& r, const float (&sc)[8], const float (&sh)[8], float (&dy)[8],
+                                              float (&zf)[8]) {
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t gpix = g * npix + pix;
+  unpack8(r.z, zf);
 #pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const int y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-    valid[d] = y < p.H && x < p.W;
+  for (int j = 0; j < 8; ++j) dy[j] = 0.f;
+  if (p.ga) {
+    unpack8(r.ga, dy);
+    if (p.mul_other) {
+      float ao[8];
+      unpack8(r.ao, ao);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dy[d][j] = 0.f, zf[d][j] = 0.f, av[d][j] = -1.f;
-    if (!valid[d]) continue;
-    const size_t pix = (((size_t)b * p.H + y) * p.W + x);
-    const size_t o = ((size_t)g * p.B * p.H * p.W + pix) * C8 + c8;
-    unpack8(p.z[o], zf[d]);
-    if (need_a) unpack8(p.a[o], av[d]);
-    if (p.ga) {
-      const size_t go = ((size_t)(p.ga_groups == 1 ? 0 : g) * p.B * p.H * p.W + pix) * p.ga_c8 + c8;
-      unpack8(p.ga[go], dy[d]);
-      if (p.mul_other) {
-        float ao[8];
-        unpack8(p.a[((size_t)(1 - g) * p.B * p.H * p.W + pix) * C8 + c8], ao);
+      for (int j = 0; j < 8; ++j) dy[j] *= ao[j];
+    }
+  }
+  if (p.gp) {
+    const uint32_t W = p.W, H = p.H, Hp = H >> 1, Wp = W >> 1;
+    const uint32_t x = pix % W, t = pix / W, y = t % H, b = t / H;
+    if ((y >> 1) < Hp && (x >> 1) < Wp) {
+      // nn.MaxPool2d backward routes the pooled gradient to the FIRST maximum of the 2x2 window in scan order;
+      // the window is re-read by its four threads (L1 hits, no extra DRAM traffic)
+      const uint32_t me = (y & 1) * 2 + (x & 1);
+      const size_t w00 = (size_t)(gpix - (y & 1) * W - (x & 1)) * C8 + c8;
+      const uint4 wv[4] = {__ldg(p.a + w00), __ldg(p.a + w00 + C8), __ldg(p.a + w00 + (size_t)W * C8),
+                           __ldg(p.a + w00 + (size_t)(W + 1) * C8)};
+      const uint4 gv = __ldg(p.gp + (size_t)(((g * p.B + b) * Hp + (y >> 1)) * Wp + (x >> 1)) * C8 + c8);
+      float m[8];
+      int best[8];
+      unpack8(wv[0], m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dy[d][j] *= ao[j];
+      for (int j = 0; j < 8; ++j) best[j] = 0;
+#pragma unroll
+      for (int d = 1; d < 4; ++d) {
+        float v[8];
+        unpack8(wv[d], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > m[j]) m[j] = v[j], best[j] = d;
       }
-    }
-  }
-  if (p.gp && qy < p.H / 2 && qx < p.W / 2) {
-    float gpv[8];
-    unpack8(p.gp[((((size_t)g * p.B + b) * (p.H / 2) + qy) * (p.W / 2) + qx) * C8 + c8], gpv);
+      float gpv[8];
+      unpack8(gv, gpv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // nn.MaxPool2d backward routes to the first maximum in window scan order
-      int best = 0;
-      float m = av[0][j];
-#pragma unroll
-      for (int d = 1; d < 4; ++d)
-        if (av[d][j] > m) m = av[d][j], best = d;
-#pragma unroll
-      for (int d = 0; d < 4; ++d)
-        if (d == best) dy[d][j] += gpv[j];
+      for (int j = 0; j < 8; ++j)
+        if (best[j] == (int)me) dy[j] += gpv[j];
     }
   }
 #pragma unroll
-  for (int d = 0; d < 4; ++d)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (!(fmaf(zf[d][j], sc[j], sh[j]) > 0.f)) dy[d][j] = 0.f;
+  for (int j = 0; j < 8; ++j)
+    if (!(fmaf(zf[j], sc[j], sh[j]) > 0.f)) dy[j] = 0.f;
 }
 
 // pass 1: partial[blk][g][c][2] = (sum dy, sum dy * xhat)
-__global__ void bn_bwd_reduce_kernel(BnBwd p, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwd p, float* __restrict__ partial) {
   extern __shared__ float sm[];  // [blockDim][16]
-  const int C8 = p.C / 8, Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2;
-  const int c8 = threadIdx.x % C8, lane_q = threadIdx.x / C8, qpb = blockDim.x / C8;
-  const size_t nquads = (size_t)p.B * Hq * Wq;
-  for (int g = 0; g < p.G; ++g) {
-    float s1[8], s2[8], mu[8], is[8];
+  constexpr int NB = 3;          // pixels in flight per thread
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
+  const uint32_t npix = (uint32_t)p.B * p.H * p.W;
+  const uint32_t stride = gridDim.x * ppb;
+  for (uint32_t g = 0; g < (uint32_t)p.G; ++g) {
+    float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
+    ld8f(p.mean + g * p.C + c8 * 8, mu);
+    ld8f(p.invstd + g * p.C + c8 * 8, is);
+    ld8f(p.scale + g * p.C + c8 * 8, sc);
+    ld8f(p.shift + g * p.C + c8 * 8, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1[j] = s2[j] = 0.f;
-      mu[j] = p.mean[g * p.C + c8 * 8 + j];
-      is[j] = p.invstd[g * p.C + c8 * 8 + j];
-    }
-    for (size_t q = (size_t)blockIdx.x * qpb + lane_q; q < nquads; q += (size_t)gridDim.x * qpb) {
-      const int qx = q % Wq, qy = (q / Wq) % Hq, b = q / ((size_t)Wq * Hq);
-      float dy[4][8], zf[4][8];
-      bool valid[4];
-      bn_bwd_dy_quad(p, g, b, qy, qx, c8, dy, zf, valid);
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    for (uint32_t q0 = blockIdx.x * ppb + lane_p; q0 < npix; q0 += NB * stride) {
+      BnBwdRaw raw[NB];
 #pragma unroll
-      for (int d = 0; d < 4; ++d)
+      for (int k = 0; k < NB; ++k)
+        if (q0 + k * stride < npix) bn_bwd_load(p, g, q0 + k * stride, c8, npix, raw[k]);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        if (q0 + k * stride >= npix) break;
+        float dy[8], zf[8];
+        bn_bwd_finish(p, g, q0 + k * stride, c8, npix, raw[k], sc, sh, dy, zf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s1[j] += dy[d][j];
-          s2[j] = fmaf(dy[d][j], (zf[d][j] - mu[j]) * is[j], s2[j]);
+          s1[j] += dy[j];
+          s2[j] = fmaf(dy[j], (zf[j] - mu[j]) * is[j], s2[j]);
         }
+      }
     }
     __syncthreads();
     float* mine = sm + threadIdx.x * 16;
@@ -396,90 +434,101 @@ __global__ void bn_bwd_reduce_kernel(BnBwd p, float* __restrict__ partial) {
     for (int i = threadIdx.x; i < p.C * 2; i += blockDim.x) {
       const int c = i >> 1, k = i & 1;
       float s = 0.f;
-      for (int l = 0; l < qpb; ++l) s += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
       dst[i] = s;
     }
   }
 }
 
-// pass 2: reduce partials; dgamma, dbeta; per-group coefficients for the apply pass
+// pass 2: reduce partials (one warp per channel); dgamma, dbeta; per-group coefficients for the apply pass
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int G, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+                                       const float* __restrict__ mean, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double dg = 0.0, db = 0.0;
   for (int g = 0; g < G; ++g) {
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-      const float* p = partial + (((size_t)b * G + g) * C + c) * 2;
-      s1 += p[0];
-      s2 += p[1];
+    for (int b = lane; b < nblk; b += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * G + g) * C + c) * 2);
+      s1 += v.x;
+      s2 += v.y;
+    }
+    for (int o = 16; o; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     dg += s2;
     db += s1;
-    coef[(g * 3 + 0) * C + c] = gamma[c] * invstd[g * C + c];  // dz = k0 * (dy - k1 - xhat * k2)
-    coef[(g * 3 + 1) * C + c] = (float)(s1 / count);
-    coef[(g * 3 + 2) * C + c] = (float)(s2 / count);
+    if (lane == 0) {
+      // dz = k0 * (dy - k1 - (z - mean) * invstd * k2)  =  k0 * dy + kz * z + kc
+      const float is = invstd[g * C + c], mu = mean[g * C + c];
+      const float k0 = gamma[c] * is, k1 = (float)(s1 / count), k2 = (float)(s2 / count);
+      coef[(g * 3 + 0) * C + c] = k0;
+      coef[(g * 3 + 1) * C + c] = -k0 * is * k2;             // kz
+      coef[(g * 3 + 2) * C + c] = -k0 * (k1 - mu * is * k2);  // kc
+    }
   }
-  dgamma[c] = (float)dg;
-  dbeta[c] = (float)db;
+  if (lane == 0) {
+    dgamma[c] = (float)dg;
+    dbeta[c] = (float)db;
+  }
 }
 
-// pass 3: dz (bf16)
-__global__ void bn_bwd_apply_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
-  const int C8 = p.C / 8, Hq = (p.H + 1) / 2, Wq = (p.W + 1) / 2;
-  const size_t total = (size_t)p.G * p.B * Hq * Wq * C8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = i % C8;
-    size_t q = i / C8;
-    const int qx = q % Wq;
-    q /= Wq;
-    const int qy = q % Hq;
-    q /= Hq;
-    const int b = q % p.B;
-    const int g = q / p.B;
-    float dy[4][8], zf[4][8];
-    bool valid[4];
-    bn_bwd_dy_quad(p, g, b, qy, qx, c8, dy, zf, valid);
-    float k0[8], k1[8], k2[8], mu[8], is[8];
+// pass 3: dz = k0 * dy + kz * z + kc   (bf16).  The linear element index is also the index into z and dz.
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
+  constexpr int NB = 4;
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t npix = (uint32_t)p.B * p.H * p.W;
+  const uint32_t total = (uint32_t)p.G * npix * C8;
+  const uint32_t stride = gridDim.x * blockDim.x;   // a multiple of C8, so c8 (and g within a batch mostly) is fixed per thread
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += NB * stride) {
+    BnBwdRaw raw[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      k0[j] = coef[(g * 3 + 0) * p.C + c];
-      k1[j] = coef[(g * 3 + 1) * p.C + c];
-      k2[j] = coef[(g * 3 + 2) * p.C + c];
-      mu[j] = p.mean[g * p.C + c];
-      is[j] = p.invstd[g * p.C + c];
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t i = i0 + k * stride;
+      if (i < total) {
+        const uint32_t gpix = i / C8, g = gpix >= npix ? 1u : 0u;
+        bn_bwd_load(p, g, gpix - g * npix, i % C8, npix, raw[k]);
+      }
     }
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      if (!valid[d]) continue;
-      const int y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-      float r[8];
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t i = i0 + k * stride;
+      if (i >= total) break;
+      const uint32_t c8 = i % C8, gpix = i / C8, g = gpix >= npix ? 1u : 0u;
+      float sc[8], sh[8], k0[8], kz[8], kc[8], dy[8], zf[8], r[8];
+      ld8f(p.scale + g * p.C + c8 * 8, sc);
+      ld8f(p.shift + g * p.C + c8 * 8, sh);
+      bn_bwd_finish(p, g, gpix - g * npix, c8, npix, raw[k], sc, sh, dy, zf);
+      ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, k0);
+      ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kz);
+      ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = k0[j] * (dy[d][j] - k1[j] - (zf[d][j] - mu[j]) * is[j] * k2[j]);
-      dz[((((size_t)g * p.B + b) * p.H + y) * p.W + x) * C8 + c8] = pack8(r);
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(k0[j], dy[j], fmaf(kz[j], zf[j], kc[j]));
+      dz[i] = pack8(r);
     }
   }
 }
 
 // ================================================================================================ decoder-input adjoint
 // dlow[b][i][j][c] = sum_{u,v} wy(u,i) wx(v,j) dcat[b][u+padT][v+padL][Cs+c]   (adjoint of bilinear x2 + pad)
-__global__ void up_input_bwd_kernel(const uint4* __restrict__ dcat, uint4* __restrict__ dlow, int B, int H, int W, int Cs,
-                                    int h, int w, int Cl) {
-  const int Ct8 = (Cs + Cl) / 8, Cs8 = Cs / 8, Cl8 = Cl / 8;
+__global__ void __launch_bounds__(256, 4)
+up_input_bwd_kernel(const uint4* __restrict__ dcat, uint4* __restrict__ dlow, int B, int H, int W, int Cs, int h, int w, int Cl) {
+  const uint32_t Ct8 = (Cs + Cl) >> 3, Cs8 = Cs >> 3, Cl8 = Cl >> 3;
   const int padT = (H - 2 * h) / 2, padL = (W - 2 * w) / 2;
   const float sy = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   const float sx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
-  const size_t total = (size_t)B * h * w * Cl8;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = idx % Cl8;
-    size_t r = idx / Cl8;
+  const uint32_t total = (uint32_t)B * h * w * Cl8;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t c8 = idx % Cl8;
+    uint32_t r = idx / Cl8;
     const int j = r % w;
     r /= w;
     const int i = r % h;
-    const int b = r / h;
+    const uint32_t b = r / h;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -497,7 +546,7 @@ __global__ void up_input_bwd_kernel(const uint4* __restrict__ dcat, uint4* __res
         const float wx = (x0 == j ? 1.f - lx : 0.f) + (x1 == j ? lx : 0.f);
         if (wx == 0.f) continue;
         float f[8];
-        unpack8(dcat[(((size_t)b * H + u + padT) * W + v + padL) * Ct8 + Cs8 + c8], f);
+        unpack8(__ldg(dcat + (size_t)((b * H + u + padT) * W + v + padL) * Ct8 + Cs8 + c8), f);
         const float ww = wy * wx;
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(ww, f[k], acc[k]);
@@ -535,7 +584,7 @@ int fabric_b200_bn_finalize(const float* stats_ws, int grid, int n_tile, int C, 
   if (!stats_ws || !gamma || !beta || !running_mean || !running_var || !scale || !shift || !mean || !invstd)
     return fail(FB_ERR_ARG, "null pointer");
   if (C % n_tile || G < 1 || G > 2 || grid < 1 || count_per_group < 1) return fail(FB_ERR_SHAPE, "bad shape");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       stats_ws, grid, n_tile, C, G, (double)count_per_group, conv_bias, gamma, beta, running_mean, running_var,
       reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift, mean, invstd);
   FB_CUDA(cudaGetLastError());
@@ -549,6 +598,7 @@ int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* sh
   if (rc) return rc;
   if (!z || !scale || !shift || !a) return fail(FB_ERR_ARG, "null pointer");
   if (C % 8) return fail(FB_ERR_SHAPE, "C must be a multiple of 8");
+  if ((double)G * B * H * W * C / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   const size_t n = (size_t)G * B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   bn_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(pool_out), G, B,
@@ -561,7 +611,7 @@ int64_t fabric_b200_seg_loss_ws_floats(int B, int H, int W) {
   const int rows = B * H;
   const int rpb = (rows + 295) / 296;
   const int nblk = (rows + rpb - 1) / rpb;
-  return (int64_t)nblk * 6 * W + 4 * (int64_t)W + 1024;
+  return (int64_t)nblk * 6 * W + 10 * (int64_t)W + 1024;
 }
 
 int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma, float eps, const float* logits,
@@ -585,7 +635,10 @@ int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma,
     FB_CUDA(cudaGetLastError());
     const size_t smem = 6 * (size_t)W * sizeof(float);
     FB_CUDA(cudaFuncSetAttribute(seg_loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_loss_finalize_kernel<<<1, 256, smem, st>>>(partial, nblk, W, label_ndim, kind, alpha, beta, eps, coef, loss_out);
+    float* sums = coef + 4 * (size_t)W;  // [6][W], inside the workspace tail
+    reduce_partials_kernel<<<(6 * W + 255) / 256, 256, 0, st>>>(partial, nblk, 6 * W, sums);
+    FB_CUDA(cudaGetLastError());
+    seg_loss_finalize_kernel<<<1, 256, smem, st>>>(sums, 1, W, label_ndim, kind, alpha, beta, eps, coef, loss_out);
     FB_CUDA(cudaGetLastError());
     seg_loss_grad_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), coef, B,
                                                                 H, W, dlogits);
@@ -635,7 +688,7 @@ int64_t fabric_b200_bn_bwd_ws_floats(int G, int C) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  return (int64_t)di.sms * 4 * G * C * 2 + (int64_t)G * 3 * C;
+  return (int64_t)di.sms * 3 * G * C * 2 + (int64_t)G * 3 * C;
 }
 
 int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga_groups, int ga_channels, int mul_other,
@@ -650,6 +703,7 @@ int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga
   if ((mul_other || gp) && !a) return fail(FB_ERR_ARG, "activation tensor needed for product / pool routing");
   if (mul_other && G != 2) return fail(FB_ERR_SHAPE, "product fusion needs both date groups");
   if (C % 8 || 256 % (C / 8) || (ga && (ga_channels % 8 || ga_channels < C))) return fail(FB_ERR_SHAPE, "bad channels");
+  if ((double)G * B * H * W * (ga ? ga_channels : C) / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   BnBwd p;
   p.z = reinterpret_cast<const uint4*>(z), p.a = reinterpret_cast<const uint4*>(a);
   p.ga = reinterpret_cast<const uint4*>(ga), p.gp = reinterpret_cast<const uint4*>(gp);
@@ -657,15 +711,14 @@ int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga
   p.ga_groups = ga_groups, p.ga_c8 = ga_channels / 8, p.mul_other = mul_other;
   p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = di.sms * 4;
+  const int nblk = di.sms * 2;   // = resident blocks (256 threads, 2 per SM): one balanced wave
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
   bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
   FB_CUDA(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, G, C, (double)B * H * W, gamma, invstd, dgamma, dbeta,
-                                                          coef);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, G, C, (double)B * H * W, gamma, invstd, mean, dgamma, dbeta, coef);
   FB_CUDA(cudaGetLastError());
-  const size_t n = (size_t)G * B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  const size_t n = (size_t)G * B * H * W * (C / 8);
   bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
   FB_CUDA(cudaGetLastError());
   return FB_OK;

@@ -82,3 +82,62 @@ def train_step(x_d1, x_d2, labels, sd, criterion):
     loss = criterion(logits, labels)
     grads = torch.autograd.grad(loss, list(P.values()), allow_unused=True)
     return loss.detach(), logits.detach(), {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(P, grads)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Teacher-forced backward oracle.
+#
+# The reference network at random init with batch-statistics BatchNorm on small batches is ill-conditioned: rounding
+# only the INPUTS of the all-fp32 reference to bf16 (a 2^-9 relative perturbation) changes its logits by 1.1 % and its
+# parameter gradients by 21-25 % (measured, config 1).  Comparing gradients of two forward passes that differ by bf16
+# storage therefore says little about the backward kernels.  This oracle removes the forward difference: it runs the
+# fp32 restatement but substitutes, at every storage point, the tensor the CUDA path actually stored (`saved`), with a
+# straight-through gradient.  fp32 autograd of that graph is exactly what the backward kernels must compute; only the
+# bf16 rounding of activation-gradients remains (< 1 % measured).
+# ------------------------------------------------------------------------------------------------------------------
+class _Force(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, value):
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def train_step_forced(x_d1, x_d2, labels, sd, criterion, saved):
+    """saved[name] -> NCHW fp32 tensor the CUDA path stored; names: '<block>.<z1|a1|z2|a2|x>.<date>'."""
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and "running_" not in k}
+
+    def force(x, name):
+        return _Force.apply(x, saved[name])
+
+    def dconv(x, pre, blk, g):
+        w1, w2 = r(P[pre + ".0.weight"]), r(P[pre + ".3.weight"])
+        z1 = force(F.conv2d(x, w1, None, padding=1), f"{blk}.z1.{g}")
+        a1 = force(F.relu(_bn_train(z1, P[pre + ".1.weight"], P[pre + ".1.bias"])), f"{blk}.a1.{g}")
+        z2 = force(F.conv2d(a1, w2, None, padding=1), f"{blk}.z2.{g}")
+        return force(F.relu(_bn_train(z2, P[pre + ".4.weight"], P[pre + ".4.bias"])), f"{blk}.a2.{g}")
+
+    def enc(x, g):
+        outs = [dconv(force(x, f"inc.x.{g}"), "inc.conv.conv", "inc", g)]
+        for n in ("down1", "down2", "down3", "down4"):
+            outs.append(dconv(F.max_pool2d(outs[-1], 2), f"{n}.mpconv.1.conv", n, g))
+        return outs
+
+    def up(x1, x2, n):
+        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return dconv(force(torch.cat([x2, x1], 1), f"{n}.x.0"), f"{n}.conv.conv", n, 0)
+
+    e1, e2 = enc(x_d1, 0), enc(x_d2, 1)
+    f = [torch.relu(a * b) for a, b in zip(e1, e2)]
+    x = up(f[4], f[3], "up1")
+    x = up(x, f[2], "up2")
+    x = up(x, f[1], "up3")
+    x = up(x, f[0], "up4")
+    logits = F.conv2d(x, P["outc.conv.weight"], P["outc.conv.bias"])
+    loss = criterion(logits, labels)
+    grads = torch.autograd.grad(loss, list(P.values()), allow_unused=True)
+    return loss.detach(), logits.detach(), {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(P, grads)}

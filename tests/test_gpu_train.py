@@ -209,7 +209,6 @@ def test_training_step_config1(cuda, golden):
     from fabric_b200 import BiDateNet
     from fabric_b200.metrics import TverskyLoss
     from oracle import bidatenet_oracle as O
-    from oracle import bidatenet_oracle_bf16 as Q
     sd = O.make_state_dict(seed=0)
     model = BiDateNet(13, 2)
     model.load_state_dict(sd)
@@ -237,11 +236,59 @@ def test_training_step_config1(cuda, golden):
             n_ref = float(golden["c1_gradnorm/" + k])
             assert abs(float(g.norm()) - n_ref) <= 0.12 * n_ref, k
     assert rel(grads["outc.conv.weight"], golden["c1_grad/outc.conv.weight"]) <= 2e-2
-    # (b) against the bf16 precision-model oracle: every gradient, including BatchNorm gamma/beta
-    _, logits_q, grads_q = Q.train_step(x1, x2, labels, sd, lambda l, t: O.tversky_loss(l, t, 0.1, 0.9))
-    assert rel(logits.detach().cpu(), logits_q) <= 2e-2
-    worst = max((rel(grads[k], grads_q[k]), k) for k in grads if not (k.endswith(".0.bias") or k.endswith(".3.bias")))
-    assert worst[0] <= 0.15, worst
+    # BatchNorm gamma/beta and all other gradients vs the fp32 reference: direction and size.  (The reference itself
+    # moves its gradients by 21-25 % when only its INPUTS are rounded to bf16 -- see oracle/bidatenet_oracle_bf16.py.)
+    for k, g in grads.items():
+        if ("c1_grad/" + k) in golden and not (k.endswith(".0.bias") or k.endswith(".3.bias")):
+            ref = golden["c1_grad/" + k].double().flatten()
+            cos = float((g.double().flatten() @ ref) / (g.double().norm() * ref.norm()))
+            assert cos >= 0.8, (k, cos)
+
+
+def _saved_as_nchw(sv):
+    out = {}
+    for blk, d in sv.items():
+        for name in ("x", "z1", "a1", "z2", "a2"):
+            t = d[name]
+            for g in range(t.shape[0]):
+                out[f"{blk}.{name}.{g}"] = t[g].float().permute(0, 3, 1, 2).cpu().contiguous()
+    return out
+
+
+@pytest.mark.parametrize("batch,size,seed", [(2, 32, 1), (3, 48, 5)])
+def test_backward_matches_teacher_forced_fp32_autograd(cuda, batch, size, seed):
+    """Whole-chain backward parity with the forward state pinned: fp32 torch autograd of the oracle graph, evaluated AT
+    the tensors the CUDA forward stored, must give the gradients the CUDA backward produced.  Only the bf16 rounding of
+    the activation gradients separates the two (stated tolerance: rel-L2 <= 3e-2 per parameter tensor, loss 1e-5)."""
+    from fabric_b200 import BiDateNet, autograd
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    from oracle import bidatenet_oracle_bf16 as Q
+    sd = O.make_state_dict(seed=0)
+    model = BiDateNet(13, 2)
+    model.load_state_dict(sd)
+    model = model.to(cuda).train()
+    x1, x2, labels = O.make_inputs(batch, size, seed=seed)
+    autograd.KEEP_SAVED = True
+    try:
+        logits = model(x1.to(cuda), x2.to(cuda))
+        saved = _saved_as_nchw(autograd.LAST_SAVED)
+    finally:
+        autograd.KEEP_SAVED, autograd.LAST_SAVED = False, None
+    loss = TverskyLoss(alpha=0.1, beta=0.9)(logits, labels.to(cuda))
+    loss.backward()
+    # the packed input has 16 channels (3 zero); the oracle graph consumes the 13 real ones
+    for g in (0, 1):
+        saved[f"inc.x.{g}"] = saved[f"inc.x.{g}"][:, :13].contiguous()
+    loss_f, logits_f, grads_f = Q.train_step_forced(x1, x2, labels, sd, lambda l, t: O.tversky_loss(l, t, 0.1, 0.9), saved)
+    assert rel(logits.detach().cpu(), logits_f) <= 1e-4          # head on identical activations: fp32 round-off only
+    assert abs(loss.item() - float(loss_f)) <= 1e-5
+    worst = (0.0, "")
+    for k, p in model.named_parameters():
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            continue
+        worst = max(worst, (rel(p.grad.detach().cpu(), grads_f[k]), k))
+    assert worst[0] <= 3e-2, worst
 
 
 def test_train_then_eval_uses_updated_running_stats(cuda):
