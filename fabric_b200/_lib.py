@@ -31,6 +31,7 @@ class Conv3x3Desc(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("pool_out", C.c_void_p), ("stats_ws", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
+        ("prod_out", C.c_void_p), ("prod_channels", C.c_int),
         ("tune", ConvTuning),
     ]
 

@@ -33,6 +33,7 @@ class BiDateNet(nn.Module):
         self.up4 = up(128, 64)
         self.outc = outconv(64, n_classes)
         self.fuse_head = True
+        self.fuse_product = True
 
     def pack_pair(self, x_d1, x_d2):
         """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16]."""
@@ -44,18 +45,41 @@ class BiDateNet(nn.Module):
 
     def forward_packed(self, x5):
         """Eval-mode forward on an already packed pair tensor; returns NCHW fp32 logits."""
-        e1 = self.inc.run5(x5, pool=True)                       # models/bidate_model.py:23,29
-        e2 = self.down1.run5(e1["pool"], pool=True)             # :24,30
-        e3 = self.down2.run5(e2["pool"], pool=True)             # :25,31
-        e4 = self.down3.run5(e3["pool"], pool=True)             # :26,32
-        e5 = self.down4.run5(e4["pool"])                        # :27,33
-        x = self.up1.run5(e5["y"], e4["y"])["y"]                # :35
-        x = self.up2.run5(x, e3["y"])["y"]                      # :36
-        x = self.up3.run5(x, e2["y"])["y"]                      # :37
+        if not getattr(self, "fuse_product", True):
+            return self._forward_packed_unfused(x5)
+        _, b, h, w, _ = x5.shape
+        dev = x5.device
+
+        def cat(level, cs, cl):     # decoder input [1,B,H/2^l,W/2^l,cs+cl]; skip half filled by the encoder epilogue
+            return torch.empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
+        cat4, cat3, cat2, cat1 = cat(0, 64, 64), cat(1, 128, 128), cat(2, 256, 256), cat(3, 512, 512)
+        e1 = self.inc.run5(x5, pool=True, prod_out=cat4)                       # models/bidate_model.py:23,29 (+ :38 skip)
+        e2 = self.down1.run5(e1["pool"], pool=True, prod_out=cat3)             # :24,30 (+ :37)
+        e3 = self.down2.run5(e2["pool"], pool=True, prod_out=cat2)             # :25,31 (+ :36)
+        e4 = self.down3.run5(e3["pool"], pool=True, prod_out=cat1)             # :26,32 (+ :35)
+        e5 = self.down4.run5(e4["pool"])                                       # :27,33
+        x = self.up1.run5(e5["y"], None, cat5=cat1)["y"]                       # :35
+        x = self.up2.run5(x, None, cat5=cat2)["y"]                             # :36
+        x = self.up3.run5(x, None, cat5=cat3)["y"]                             # :37
         if self.fuse_head:
-            return self.up4.run5(x, e1["y"], head=self.outc.head(), keep_main=False)["logits"]   # :38-39
-        x = self.up4.run5(x, e1["y"])["y"]                      # :38
-        return self.outc.run5(x)                                # :39
+            return self.up4.run5(x, None, cat5=cat4, head=self.outc.head(), keep_main=False)["logits"]   # :38-39
+        x = self.up4.run5(x, None, cat5=cat4)["y"]                             # :38
+        return self.outc.run5(x)                                               # :39
+
+    def _forward_packed_unfused(self, x5):
+        """Same network with the decoder inputs built by the stand-alone kernel (cross-check of the fused epilogue)."""
+        e1 = self.inc.run5(x5, pool=True)
+        e2 = self.down1.run5(e1["pool"], pool=True)
+        e3 = self.down2.run5(e2["pool"], pool=True)
+        e4 = self.down3.run5(e3["pool"], pool=True)
+        e5 = self.down4.run5(e4["pool"])
+        x = self.up1.run5(e5["y"], e4["y"])["y"]
+        x = self.up2.run5(x, e3["y"])["y"]
+        x = self.up3.run5(x, e2["y"])["y"]
+        if self.fuse_head:
+            return self.up4.run5(x, e1["y"], head=self.outc.head(), keep_main=False)["logits"]
+        x = self.up4.run5(x, e1["y"])["y"]
+        return self.outc.run5(x)
 
     def forward(self, x_d1, x_d2):
         if x_d1.shape != x_d2.shape:

@@ -29,6 +29,8 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (d->head_out && (d->Cout != 64 || n_tile != 64 || !d->head_w || !d->head_b))
     return fail(FB_ERR_SHAPE, "fused head needs Cout == 64 and head weights");
   if (!d->store_main && !d->head_out) return fail(FB_ERR_ARG, "nothing to write");
+  if (d->prod_out && (d->G != 2 || !d->store_main || d->prod_channels < d->Cout || d->prod_channels % 8))
+    return fail(FB_ERR_SHAPE, "product fusion needs both date groups, the main output and prod_channels >= Cout");
 
   fb::Conv3x3Params& p = pl->p;
   memset(&p, 0, sizeof(p));
@@ -49,7 +51,8 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (halo < 0) halo = halo_ok ? 1 : 0;
   if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs Cin %% 64 == 0 and H > 8");
 
-  const long long total = (long long)p.num_m_tiles * p.num_n_tiles;
+  // in date-pair mode the persistent loop runs over units (spatial tile x N tile), each = 2 tiles
+  const long long total = (long long)p.num_m_tiles * p.num_n_tiles / (d->prod_out ? 2 : 1);
   int grid = d->tune.grid > 0 ? d->tune.grid : di.sms;
   if (grid > total) grid = (int)total;
   else grid = (grid / p.num_n_tiles) * p.num_n_tiles;  // each CTA keeps one N tile for its whole life
@@ -60,7 +63,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
 
   const int a_bytes = fb::conv_a_stage_bytes(ck, halo);
   const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck);
-  const int fixed = 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile) + 1024;
+  // product fusion keeps the date-0 tile in a second staging buffer when the N tile is small enough
+  const int out_bufs = (d->prod_out && n_tile <= 128) ? 2 : 1;
+  const int fixed = out_bufs * 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile) + 1024;
   const int avail = di.smem_optin - fixed;
   const int kblocks = 9 * p.kchunks;
   int b_res = d->tune.b_resident;
@@ -94,6 +99,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   p.pool_out = reinterpret_cast<__nv_bfloat16*>(d->pool_out);
   p.stats_out = d->stats_ws;
   p.head_w = d->head_w, p.head_b = d->head_b, p.head_out = d->head_out;
+  p.prod_out = reinterpret_cast<__nv_bfloat16*>(d->prod_out), p.prod_ct = d->prod_channels, p.y0_ptr = d->y;
+  p.pair_dates = d->prod_out ? 1 : 0;
+  p.out_bufs = out_bufs;
   pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem;
   return FB_OK;
 }
@@ -180,14 +188,18 @@ build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ 
                       int W, int Cs, int h, int w, int Cl, int low_groups) {
   const uint32_t Ct8 = (Cs + Cl) >> 3, Cs8 = Cs >> 3, Cl8 = Cl >> 3;
   const uint32_t npix = (uint32_t)B * H * W;
-  const uint32_t total = npix * Ct8;
+  // skip == nullptr: the skip half was already written by the encoder conv's fused product epilogue -> only the
+  // upsampled channels [Cs, Cs+Cl) are produced here
+  const uint32_t per_pix = skip ? Ct8 : Cl8;
+  const uint32_t total = npix * per_pix;
   const uint32_t skip_g = npix * Cs8;  // one date group of skip, in uint4
   const uint32_t low_g = (uint32_t)B * h * w * Cl8;
   const int padT = (H - 2 * h) / 2, padL = (W - 2 * w) / 2;
   const float sy = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
   const float sx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t c8 = i % Ct8, pix = i / Ct8;
+    const uint32_t pix = i / per_pix;
+    const uint32_t c8 = skip ? i % per_pix : Cs8 + i % per_pix;
     float r[8];
     if (c8 < Cs8) {
       const uint32_t o = pix * Cs8 + c8;
@@ -231,7 +243,7 @@ build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ 
         }
       }
     }
-    out[i] = fb::pack8(r);
+    out[pix * Ct8 + c8] = fb::pack8(r);
   }
 }
 
@@ -389,11 +401,11 @@ int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  if (!skip || !low || !out) return fail(FB_ERR_ARG, "null pointer");
+  if (!low || !out) return fail(FB_ERR_ARG, "null pointer");
   if (Cs % 8 || Cl % 8 || 2 * h > H || 2 * w > W || (low_groups != 1 && low_groups != 2)) return fail(FB_ERR_SHAPE, "bad shape");
   if ((double)B * H * W * (Cs + Cl) / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   if (!aligned16(skip) || !aligned16(low) || !aligned16(out)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
-  const size_t n = (size_t)B * H * W * (Cs + Cl) / 8;
+  const size_t n = (size_t)B * H * W * (skip ? Cs + Cl : Cl) / 8;
   build_up_input_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(skip), reinterpret_cast<const uint4*>(low), reinterpret_cast<uint4*>(out), B, H, W, Cs,
       h, w, Cl, low_groups);

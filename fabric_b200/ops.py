@@ -116,7 +116,7 @@ DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, 
 def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False, pool: bool = False, stats: bool = False,
             head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None,
-            true_cin: Optional[int] = None):
+            true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None):
     """3x3 pad-1 convolution on tcgen05 (see include/fabric_b200.h: fabric_b200_conv3x3).
 
     Returns a dict with ``y`` [G,B,H,W,cout] bf16 and optionally ``pool`` [G,B,H/2,W/2,cout],
@@ -148,6 +148,10 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
         hw, hb = head
         res["logits"] = torch.empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
         d.head_w, d.head_b, d.head_out = _p(hw), _p(hb), _p(res["logits"])
+    if prod_out is not None:
+        # fused relu(y[date 1] * y[date 0]) into channels [0, cout) of the decoder input [1,B,H,W,Ct]
+        assert g == 2 and prod_out.shape[:4] == (1, b, h, w) and prod_out.dtype == torch.bfloat16
+        d.prod_out, d.prod_channels = _p(prod_out), prod_out.shape[4]
     if stats:
         # the workspace size depends on the grid the planner picks; the planner ignores the pointer value
         d.stats_ws = 1
@@ -170,15 +174,21 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
     return res
 
 
-def build_up_input(skip5: torch.Tensor, low5: torch.Tensor) -> torch.Tensor:
+def build_up_input(skip5: Optional[torch.Tensor], low5: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cat([relu(skip_d2*skip_d1), pad(bilinear_x2(low))], C) as one kernel.  skip5 [2,B,H,W,Cs];
-    low5 [2,B,h,w,Cl] (product of both dates, up1) or [1,B,h,w,Cl].  Returns [1,B,H,W,Cs+Cl]."""
-    _need_cuda(skip5, low5)
-    assert skip5.shape[0] == 2
-    _, b, h_, w_, cs = skip5.shape
-    lg, b2, h, w, cl = low5.shape
-    assert b2 == b
-    out = torch.empty((1, b, h_, w_, cs + cl), dtype=torch.bfloat16, device=skip5.device)
+    low5 [2,B,h,w,Cl] (product of both dates, up1) or [1,B,h,w,Cl].  Returns [1,B,H,W,Cs+Cl].
+    With ``skip5=None`` and ``out`` given, only the upsampled channels [Cs, Cs+Cl) of ``out`` are written (the skip half
+    was produced by the encoder conv's fused product epilogue)."""
+    _need_cuda(skip5, low5, out)
+    lg, b, h, w, cl = low5.shape
+    if skip5 is not None:
+        assert skip5.shape[0] == 2 and skip5.shape[1] == b
+        _, _, h_, w_, cs = skip5.shape
+        out = torch.empty((1, b, h_, w_, cs + cl), dtype=torch.bfloat16, device=low5.device)
+    else:
+        assert out is not None and out.shape[1] == b
+        _, _, h_, w_, ct = out.shape
+        cs = ct - cl
     check(_lib.load().fabric_b200_build_up_input(_p(skip5), _p(low5), _p(out), b, h_, w_, cs, h, w, cl, lg, _stream()),
           "build_up_input")
     _count()

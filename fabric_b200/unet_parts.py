@@ -75,7 +75,7 @@ class double_conv(nn.Module):
         return self._cache().get(("bn", idx), [bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias],
                                  lambda: ops.bn_fold_eval(bn, conv.bias), extra=bn.__dict__.get("_fb_stats_epoch", 0))
 
-    def run5(self, x5, pool=False, head=None, keep_main=True):
+    def run5(self, x5, pool=False, head=None, keep_main=True, prod_out=None):
         """NHWC5 bf16 in -> dict(y=..., pool=..., logits=...).  Eval mode: BatchNorm (running statistics), the conv
         bias and ReLU ride in the conv epilogue; ``pool`` adds the fused MaxPool2d(2) copy for the next ``down``;
         ``head`` = (weight[2,64], bias[2]) fuses ``outconv`` into the second conv."""
@@ -85,7 +85,7 @@ class double_conv(nn.Module):
         s2, h2 = self._folded(3)
         mid = ops.conv3x3(x5, self._packed(0), self.out_ch, s1, h1, relu=True, tune=self.tune1, true_cin=self.in_ch)["y"]
         return ops.conv3x3(mid, self._packed(3), self.out_ch, s2, h2, relu=True, pool=pool, head=head,
-                           store_main=keep_main, tune=self.tune2)
+                           store_main=keep_main, tune=self.tune2, prod_out=prod_out)
 
     def forward(self, x):
         x5 = ops.pack_input(x, c_pad=ops.cpad(self.in_ch)).unsqueeze(0)
@@ -142,10 +142,14 @@ class up(nn.Module):
         self.up = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
         self.conv = double_conv(in_ch, out_ch)
 
-    def run5(self, low5, skip5, **kw):
+    def run5(self, low5, skip5, cat5=None, **kw):
         """low5: [2,B,h,w,C] (both dates; their product is taken on the fly) or [1,B,h,w,C];
-        skip5: [2,B,H,W,Cs] encoder activations of both dates (relu(d2*d1) is fused)."""
-        cat5 = ops.build_up_input(skip5, low5)
+        skip5: [2,B,H,W,Cs] encoder activations of both dates (relu(d2*d1) is fused), or None when ``cat5`` already
+        holds the fused skip half (written by the encoder conv's product epilogue)."""
+        if skip5 is not None:
+            cat5 = ops.build_up_input(skip5, low5)
+        else:
+            ops.build_up_input(None, low5, out=cat5)
         return self.conv.run5(cat5, **kw)
 
     def forward(self, x1, x2):

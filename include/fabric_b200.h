@@ -77,6 +77,9 @@ typedef struct {
   const float* head_w; /* NULL or fp32 [2][64]: fused outconv 1x1 (unet_parts.py:86), needs Cout == 64 */
   const float* head_b; /* fp32 [2] */
   float* head_out;     /* fp32 NCHW [G*B][2][H][W] */
+  void* prod_out;      /* NULL or bf16 [B][H][W][prod_channels]: fused relu(y[date 1] * y[date 0]) written into
+                          channels [0, Cout) -- the skip half of the decoder input (bidate_model.py:35-38); G == 2 */
+  int prod_channels;
   fb_conv_tuning tune;
 } fb_conv3x3_desc;
 
@@ -102,7 +105,8 @@ int fabric_b200_bn_fold_eval(const float* gamma, const float* beta, const float*
  * (models/bidate_model.py:35-38 + models/unet_parts.py:56-58,65-78):
  *   out[b][y][x][0:Cs]      = skip[0][b][y][x][:] * skip[1][b][y][x][:]
  *   out[b][y][x][Cs:Cs+Cl]  = bilinear(align_corners=True) of low, zero outside the padded window
- * low has low_groups = 2 (low = product of the two dates, up1) or 1 (previous decoder stage). */
+ * low has low_groups = 2 (low = product of the two dates, up1) or 1 (previous decoder stage).
+ * skip == NULL: only the upsampled channels are written (the skip half came from fabric_b200_conv3x3's prod_out). */
 int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int B, int H, int W, int Cs, int h, int w,
                                int Cl, int low_groups, void* stream);
 

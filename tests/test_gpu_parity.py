@@ -126,6 +126,38 @@ def test_conv3x3_linearity_and_halo_equals_tap(cuda):
     assert torch.equal(a, c)
 
 
+@pytest.mark.parametrize("H,W,cin,cout,tune", [(32, 32, 64, 64, dict()), (45, 45, 64, 128, dict()), (20, 12, 128, 256, dict()),
+                                                (8, 8, 64, 64, dict()), (32, 24, 64, 64, dict(grid=4))])
+def test_conv3x3_fused_date_product(cuda, H, W, cin, cout, tune):
+    """relu(y[date 1] * y[date 0]) (reference bidate_model.py:35-38) fused into the conv epilogue == product of the
+    stored outputs, bit-exact; the conv outputs themselves are unchanged by the pair scheduling."""
+    from fabric_b200 import ops
+    torch.manual_seed(11)
+    B = 3
+    x5 = torch.randn(2, B, H, W, cin, device=cuda).bfloat16()
+    wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5), 0)
+    cat = torch.full((1, B, H, W, cout + 64), 7.0, device=cuda, dtype=torch.bfloat16)
+    plain = ops.conv3x3(x5, wp, cout, relu=True, tune=tune)["y"]
+    fused = ops.conv3x3(x5, wp, cout, relu=True, tune=tune, prod_out=cat, pool=True, stats=True)
+    assert torch.equal(fused["y"], plain)
+    assert torch.equal(cat[0, ..., :cout], torch.relu(plain[0].float() * plain[1].float()).bfloat16())
+    assert bool((cat[0, ..., cout:] == 7.0).all())                 # the upsample half is left untouched
+
+
+def test_fused_and_unfused_decoder_inputs_agree(cuda):
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, O.make_state_dict(seed=0))
+    for (b, s, seed) in ((2, 32, 1), (1, 90, 2), (2, 128, 3)):
+        x1, x2, _ = O.make_inputs(b, s, seed=seed)
+        with torch.no_grad():
+            model.fuse_product = True
+            a = model(x1.to(cuda), x2.to(cuda))
+            model.fuse_product = False
+            c = model(x1.to(cuda), x2.to(cuda))
+        model.fuse_product = True
+        assert torch.equal(a, c)
+
+
 def test_pack_unpack_roundtrip(cuda):
     from fabric_b200 import ops
     x = torch.randn(3, 13, 37, 70, device=cuda)
