@@ -168,12 +168,80 @@ def config_dict(workload, n):
             "cache": "inputs (2 x 218 MB fp32) and activations (> 1 GB per layer) exceed the 126 MB L2; no flush needed"}
 
 
+def run_scene(args, dev, rank, world):
+    """BASELINE configs[4]: full-scene tiled inference, 13-band S x S bi-date scene, 256 window, reference tiling
+    (non-overlapping + last row / column / corner, utils/inference.py:134-236), tiles sharded over ranks."""
+    import torch
+    import torch.distributed as dist
+    from fabric_b200 import BiDateNet, ops
+    from fabric_b200.scene import predict_scene, tile_origins
+    S = args.scene
+    torch.manual_seed(0)
+    model = BiDateNet(13, 2).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)          # same scene on every rank (it is one job)
+    d1 = torch.randn(13, S, S, device=dev, generator=g)
+    d2 = torch.randn(13, S, S, device=dev, generator=g)
+    n_tiles = len(tile_origins(S, S, SIZE)[0])
+
+    def step():
+        return predict_scene(model, d1, d2, patch_size=SIZE, batch_size=PAIRS, rank=rank, world=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        step()
+    barrier()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        canvas, info = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    # end to end: host scene (pinned) -> device, predict, mask back to the host
+    e2e = None
+    if S <= 12000:
+        h1, h2 = d1.cpu().pin_memory(), d2.cpu().pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        a, b = h1.to(dev, non_blocking=True), h2.to(dev, non_blocking=True)
+        canvas, _ = predict_scene(model, a, b, patch_size=SIZE, batch_size=PAIRS, rank=rank, world=world)
+        host_mask = canvas.cpu() if canvas is not None else None
+        barrier()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_tiles / float(tt.item()), "unit": "patch-pairs/s", "h2d_bytes_per_step": 2 * h1.numel() * 4,
+               "d2h_bytes_per_step": S * S, "steps": 1,
+               "api": "fabric_b200.scene.predict_scene (pinned fp32 scene in, uint8 change mask out)"}
+        del host_mask
+    if rank == 0:
+        print(json.dumps({
+            "metric": "patch-pairs/s (13x256x256)", "value": n_tiles / (ms / 1e3), "unit": "patch-pairs/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"full-scene tiled inference, 13-band {S}x{S} bi-date scene, 256 window, reference "
+                                   f"tiling ({n_tiles} tiles), batches of {PAIRS} tiles sharded over {world} GPU(s)",
+                       "tiles": n_tiles, "scene": [13, S, S], "parallelism": f"tile-parallel x{world}"},
+            "e2e": e2e, "gpu_launches": ops.LAUNCHES - l0, "roofline": None, "cpu_baseline": None, "clocks": None,
+        }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "scene"])
+    ap.add_argument("--scene", type=int, default=10000, help="scene side for --workload scene (BASELINE configs[4])")
     ap.add_argument("--impl", default="fabric_b200", choices=["fabric_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -181,6 +249,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     if args.impl == "reference":
+        if args.workload == "scene":
+            args.workload = "infer"       # the reference's scene loop is its eval forward per batch of patches
         run_reference_arm(args)
         return
 
@@ -198,6 +268,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.workload == "scene":
+        run_scene(args, dev, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     torch.manual_seed(0)
     train = args.workload == "train"
@@ -219,8 +295,7 @@ def main():
             optimizer.zero_grad(set_to_none=True)
             loss = criterion(model(a, b), lab)
             loss.backward()
-            dp.sync()                                                 # ONE NCCL all-reduce (no-op for N = 1)
-            optimizer.step()
+            dp.sync_and_step(1e-3)     # ONE NCCL all-reduce (skipped for N = 1) + ONE fused SGD kernel (train.py:95)
             return loss
     else:
         model.eval()

@@ -331,3 +331,50 @@ def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: in
     check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
     _count(2)
     return dw
+
+
+# ------------------------------------------------------------------------------------------------ scene ops
+def gather_tiles(scene: torch.Tensor, origins: torch.Tensor, p: int, mean=None, inv_std=None, c_pad: Optional[int] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scene [C,H,W] fp32 / uint16 (device) -> tiles bf16 [N,p,p,Cpad] at origins int32 [N,2] (row, col)."""
+    _need_cuda(scene, origins, mean, inv_std, out)
+    c, h, w = scene.shape
+    n = origins.shape[0]
+    c_pad = c_pad or cpad(c)
+    dt = {torch.float32: 0, torch.uint16: 1}.get(scene.dtype)
+    if dt is None:
+        raise _lib.FabricB200Error("scene must be float32 or uint16")
+    assert origins.dtype == torch.int32
+    if out is None:
+        out = torch.empty((n, p, p, c_pad), dtype=torch.bfloat16, device=scene.device)
+    check(_lib.load().fabric_b200_gather_tiles(_p(scene), dt, _p(origins), _p(out), _p(mean), _p(inv_std), n, c, c_pad, h, w, p,
+                                               _stream()), "gather_tiles")
+    _count()
+    return out
+
+
+def argmax_metrics(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, want_mask: bool = True,
+                   counts: Optional[torch.Tensor] = None):
+    """torch.max(logits,1) indices as uint8 [B,H,W] and (with labels) confusion counts (TP, FP, FN, TN) accumulated
+    into `counts` (uint64 [4], device)."""
+    _need_cuda(logits, labels, counts)
+    b, _, h, w = logits.shape
+    mask = torch.empty((b, h, w), dtype=torch.uint8, device=logits.device) if want_mask else None
+    if labels is not None:
+        if counts is None:
+            counts = torch.zeros(4, dtype=torch.int64, device=logits.device)
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+    check(_lib.load().fabric_b200_argmax_metrics(_p(logits), _p(labels), _p(mask), _p(counts), b, h, w, _stream()),
+          "argmax_metrics")
+    _count()
+    return mask, counts
+
+
+def scatter_tiles(masks: torch.Tensor, origins: torch.Tensor, canvas: torch.Tensor, first: int, count: int):
+    _need_cuda(masks, origins, canvas)
+    n, p, _ = masks.shape
+    h, w = canvas.shape
+    check(_lib.load().fabric_b200_scatter_tiles(_p(masks), _p(origins), _p(canvas), first, count, p, h, w, _stream()),
+          "scatter_tiles")
+    _count()

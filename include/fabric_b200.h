@@ -179,6 +179,32 @@ int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream);
 /* sum the split-K partials and transpose to nn.Conv2d layout: dw [Cout][Cin][3][3] fp32 */
 int fabric_b200_wgrad_reduce(const float* ws, int splits, int Cout, int Cin, int CinPad, float* dw, void* stream);
 
+/* ---- full-scene inference (reference utils/inference.py, utils/dataloaders.py:94-99, train.py:96-106) -- */
+
+/* Tile gather: scene [C][H][W] (scene_dtype 0 = fp32, 1 = uint16 raw Sentinel-2 digital numbers) -> packed tiles
+ * bf16 [N][p][p][Cpad]; tile n starts at (origins[2n], origins[2n+1]) = (row, col).  With mean / inv_std (per band)
+ * the z-score (v - mean[c]) * inv_std[c] of city_loader (dataloaders.py:94-99) is applied on the fly.  Replaces
+ * _get_patches' host-side extract/vstack (inference.py:134-181) + the NCHW transpose + the layout pack. */
+int fabric_b200_gather_tiles(const void* scene, int scene_dtype, const int* origins, void* dst, const float* mean,
+                             const float* inv_std, int N, int C, int Cpad, int H, int W, int p, void* stream);
+/* torch.max(logits, 1) indices (train.py:96,138,199; ties -> class 0) as uint8 mask (nullable), and with labels
+ * (nullable) the confusion counts of the positive class accumulated into counts[4] = (TP, FP, FN, TN) -- what
+ * sklearn prfs(average='binary') is computed from at train.py:103-106. */
+int fabric_b200_argmax_metrics(const float* logits, const int64_t* labels, uint8_t* mask, uint64_t* counts, int B, int H, int W,
+                               void* stream);
+/* _get_bands (inference.py:184-236): write tiles [first, first+count) of masks uint8 [N][p][p] into canvas uint8
+ * [H][W] at their origins.  The caller launches one call per tile class (grid, last column, last row, corner) in that
+ * order, which reproduces the reference's "later write wins" rule deterministically. */
+int fabric_b200_scatter_tiles(const uint8_t* masks, const int* origins, uint8_t* canvas, int first, int count, int p, int H,
+                              int W, void* stream);
+
+/* Plain SGD p -= lr * grad_scale * g over many tensors in ONE launch (reference train.py:55,95:
+ * optim.SGD(model.parameters(), lr), no momentum / weight decay).  `chunks` is a DEVICE array of n_chunks records
+ * {float* p; const float* g; int32 n; int32 pad} (16-byte records, <= 65536 elements each): one CTA per record.
+ * With grad_scale = 1/world and g pointing into the all-reduced bucket this is the optimizer step fused behind the
+ * single NCCL all-reduce. */
+int fabric_b200_sgd_step(const void* chunks, int n_chunks, float lr, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

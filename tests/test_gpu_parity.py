@@ -295,3 +295,61 @@ def test_host_pipeline_matches_direct_call(cuda):
     assert torch.equal(logits, direct)
     mask = predict_patches(model, x1.numpy(), x2.numpy(), batch_size=2, return_logits=False)
     assert torch.equal(mask, direct.argmax(1).to(torch.uint8))
+
+
+# ------------------------------------------------------------------------------------------------ scene tiling (8f)
+def test_gather_argmax_scatter_match_oracle(cuda):
+    """device gather (+ fused z-score, fp32 and uint16 scenes) == oracle get_patches; argmax/metrics == torch;
+    reassembly == oracle get_bands including the later-write-wins overlaps"""
+    import numpy as np
+    from fabric_b200 import ops
+    from fabric_b200.scene import SceneTiler
+    from oracle import bidatenet_oracle as O
+    torch.manual_seed(13)
+    h, w, p = 200, 150, 64
+    raw = torch.randint(0, 4000, (13, h, w), dtype=torch.int32)
+    mean, std = torch.rand(13) * 2000 + 500, torch.rand(13) * 900 + 100
+    scene = ((raw.float() - mean[:, None, None]) / std[:, None, None])
+    tiler = SceneTiler(h, w, p, cuda)
+    ref_patches, hs, ws, lc, lr, _, _ = O.get_patches(scene.permute(1, 2, 0).numpy(), p)     # [N,p,p,13]
+    refq = torch.from_numpy(ref_patches).bfloat16().float()
+    t32 = tiler.gather(scene.to(cuda), 0, tiler.n)
+    assert t32.shape == (tiler.n, p, p, 16)
+    assert torch.equal(t32[..., :13].float().cpu(), refq) and torch.count_nonzero(t32[..., 13:]) == 0
+    t16 = tiler.gather(raw.to(torch.uint16).to(cuda), 0, tiler.n, mean.to(cuda), (1.0 / std).to(cuda))
+    assert ((t16[..., :13].float().cpu() - refq).abs() <= 2 ** -7 * refq.abs() + 1e-6).all()
+    # argmax + confusion counts
+    logits = torch.randn(tiler.n, 2, p, p, device=cuda)
+    logits[0, :, 0, :8] = 0.0                                        # ties -> class 0 like torch.max
+    labels = (torch.rand(tiler.n, p, p, device=cuda) < 0.3).long()
+    mask, counts = ops.argmax_metrics(logits, labels)
+    pred = torch.max(logits, 1)[1]
+    assert torch.equal(mask.long(), pred)
+    tp = int(((pred == 1) & (labels == 1)).sum()); fp = int(((pred == 1) & (labels == 0)).sum())
+    fn = int(((pred == 0) & (labels == 1)).sum()); tn = int(((pred == 0) & (labels == 0)).sum())
+    assert counts.tolist() == [tp, fp, fn, tn]
+    # reassembly with overlaps
+    canvas = tiler.reassemble(mask)
+    ref_canvas = O.get_bands(mask.cpu().numpy().astype(np.float64), hs, ws, lc, lr, h, w, p)
+    assert np.array_equal(canvas.cpu().numpy().astype(np.float64), ref_canvas)
+
+
+def test_predict_scene_matches_reference_pipeline(cuda):
+    """whole config-5 pipeline on a small scene vs oracle: get_patches -> BiDateNet (fp32 oracle) -> argmax -> get_bands"""
+    import numpy as np
+    from fabric_b200.scene import predict_scene
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    model = _model(cuda, sd)
+    g = torch.Generator().manual_seed(17)
+    h, w, p = 150, 100, 64
+    d1, d2 = torch.randn(13, h, w, generator=g), torch.randn(13, h, w, generator=g)
+    canvas, info = predict_scene(model, d1.to(cuda), d2.to(cuda), patch_size=p, batch_size=4)
+    p1, hs, ws, lc, lr, _, _ = O.get_patches(d1.permute(1, 2, 0).numpy(), p)
+    p2 = O.get_patches(d2.permute(1, 2, 0).numpy(), p)[0]
+    assert info["tiles"] == p1.shape[0]
+    with torch.no_grad():
+        logits = O.bidatenet_forward(torch.from_numpy(p1).permute(0, 3, 1, 2), torch.from_numpy(p2).permute(0, 3, 1, 2), sd)
+    ref = O.get_bands(torch.max(logits, 1)[1].numpy().astype(np.float64), hs, ws, lc, lr, h, w, p)
+    agree = (canvas.cpu().numpy().astype(np.float64) == ref).mean()
+    assert agree >= 0.999, agree

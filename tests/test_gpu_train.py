@@ -313,3 +313,36 @@ def test_train_then_eval_uses_updated_running_stats(cuda):
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     ref = O.bidatenet_forward(x1.cpu(), x2.cpu(), sd, training=False)
     assert rel(after.cpu(), ref) <= 1e-2
+
+
+def test_fused_sgd_step_equals_torch_sgd(cuda):
+    """DataParallelStep.sync_and_step == dp.sync(); torch.optim.SGD(lr).step() (reference train.py:55,95), and the next
+    forward sees the updated weights (packed-weight caches are invalidated)."""
+    import copy
+    from fabric_b200 import BiDateNet
+    from fabric_b200.distributed import DataParallelStep
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    x1, x2, labels = O.make_inputs(2, 32, seed=3)
+    x1, x2, labels = x1.to(cuda), x2.to(cuda), labels.to(cuda)
+    crit = TverskyLoss(alpha=0.1, beta=0.9)
+    outs = []
+    for fused in (False, True):
+        model = BiDateNet(13, 2)
+        model.load_state_dict(sd)
+        model = model.to(cuda).train()
+        dp = DataParallelStep(model)
+        opt = torch.optim.SGD(model.parameters(), lr=0.5)
+        crit(model(x1, x2), labels).backward()
+        if fused:
+            dp.sync_and_step(0.5)
+        else:
+            dp.sync()
+            opt.step()
+        model.eval()
+        with torch.no_grad():
+            outs.append((copy.deepcopy(model.state_dict()), model(x1, x2).clone()))
+    for k in outs[0][0]:
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    assert torch.equal(outs[0][1], outs[1][1])

@@ -102,3 +102,17 @@ def test_bf16_precision_model_oracle_brackets_the_reference(golden):
     kb = "down3.mpconv.1.conv.1.bias"
     e = float((grads[kb] - golden["c1_grad/" + kb]).norm() / golden["c1_grad/" + kb].norm())
     assert 0.05 < e < 1.0
+
+
+def test_tile_origins_match_oracle_tiler():
+    """pure host logic: same tile order / counts as reference `_get_patches` (via the oracle restatement)"""
+    import numpy as np
+    from fabric_b200.scene import tile_origins
+    from oracle import bidatenet_oracle as O
+    for (h, w, p) in ((200, 150, 64), (128, 128, 64), (130, 70, 32), (64, 64, 64)):
+        idx = np.arange(h * w, dtype=np.float32).reshape(h, w, 1)
+        patches, hs, ws, lc, lr, _, _ = O.get_patches(idx, p)
+        org, hs2, ws2, lc2, lr2 = tile_origins(h, w, p)
+        assert (hs, ws, lc, lr) == (hs2, ws2, lc2, lr2) and len(org) == patches.shape[0]
+        for k, (y, x) in enumerate(org):
+            assert patches[k, 0, 0, 0] == y * w + x
