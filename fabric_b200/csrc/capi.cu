@@ -47,9 +47,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   p.num_n_tiles = d->Cout / n_tile;
   p.kchunks = d->Cin / ck;
   int halo = d->tune.halo;
-  const bool halo_ok = (ck == 64 && p.bh == 16);
+  const bool halo_ok = (p.bh == 16);
   if (halo < 0) halo = halo_ok ? 1 : 0;
-  if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs Cin %% 64 == 0 and H > 8");
+  if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs H > 8");
 
   // in date-pair mode the persistent loop runs over units (spatial tile x N tile), each = 2 tiles
   const long long total = (long long)p.num_m_tiles * p.num_n_tiles / (d->prod_out ? 2 : 1);
@@ -64,6 +64,8 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   const int a_bytes = fb::conv_a_stage_bytes(ck, halo);
   const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck);
   // product fusion keeps the date-0 tile in a second staging buffer when the N tile is small enough
+  // (measured: a second buffer does NOT help ordinary tiles -- the previous store has long drained -- and costs the
+  //  128->64 layers their resident weights, so it is used for product pairs only)
   const int out_bufs = (d->prod_out && n_tile <= 128) ? 2 : 1;
   const int fixed = out_bufs * 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile) + 1024;
   const int avail = di.smem_optin - fixed;
@@ -79,7 +81,7 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (b_res) {
     b_st = kblocks;
     if (a_st <= 0) a_st = (avail - b_st * b_bytes) / a_bytes;
-    if (a_st > 4) a_st = 4;
+    if (a_st > 8) a_st = 8;   // weights resident: all remaining smem prefetches input tiles (HBM latency)
   } else if (halo) {
     if (a_st <= 0) a_st = 2;
     if (b_st <= 0) b_st = (avail - a_st * a_bytes) / b_bytes;
@@ -101,6 +103,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   p.head_w = d->head_w, p.head_b = d->head_b, p.head_out = d->head_out;
   p.prod_out = reinterpret_cast<__nv_bfloat16*>(d->prod_out), p.prod_ct = d->prod_channels, p.y0_ptr = d->y;
   p.pair_dates = d->prod_out ? 1 : 0;
+  auto magic = [](int dv) { return (unsigned long long)(((1ULL << 40) + dv - 1) / dv); };
+  p.mg_nt = magic(p.num_n_tiles), p.mg_tx = magic(p.tiles_x), p.mg_ty = magic(p.tiles_y), p.mg_tb = magic(p.tiles_b);
+  if ((double)p.num_m_tiles * p.num_n_tiles * 65536.0 >= 1.0e12) return fail(FB_ERR_SHAPE, "too many tiles");
   p.out_bufs = out_bufs;
   pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem;
   return FB_OK;
@@ -356,13 +361,15 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   const fb::Conv3x3Params& p = pl.p;
   const CUtensorMapSwizzle sw_a = pl.ck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap tA, tB, tY;
-  if (pl.halo) rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, 64, fb::kHaloW, fb::kHaloH, 1, sw_a);
+  if (pl.halo) rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, pl.ck, fb::kHaloW, fb::kHaloH, 1, sw_a);
   else rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, pl.ck, 8, p.bh, p.bn, sw_a);
   if (rc) return rc;
   rc = make_tmap_2d(&tB, d->w, p.Cout, 9LL * p.Cin, pl.n_tile, pl.ck, sw_a);
   if (rc) return rc;
   // y may be absent (head-only): the map is still needed as a kernel argument, point it at x's storage
-  if (d->store_main) rc = make_tmap_act(&tY, d->y, p.Cout, p.W, p.H, p.B, p.G, 64, 8, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  // store box = one epilogue warp's 32 pixel rows
+  const int bhw = p.bh < 4 ? p.bh : 4;
+  if (d->store_main) rc = make_tmap_act(&tY, d->y, p.Cout, p.W, p.H, p.B, p.G, 64, 8, bhw, 4 / bhw, CU_TENSOR_MAP_SWIZZLE_128B);
   else tY = tA;
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -370,6 +377,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
 #define FB_DISPATCH(NT, CK, HL, RS) \
   if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) return launch_conv<NT, CK, HL, RS>(pl, tA, tB, tY, st);
   FB_DISPATCH(64, 16, false, true)
+  FB_DISPATCH(64, 16, true, true)
   FB_DISPATCH(64, 64, false, false)
   FB_DISPATCH(64, 64, false, true)
   FB_DISPATCH(64, 64, true, false)

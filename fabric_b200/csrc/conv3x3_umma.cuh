@@ -47,6 +47,7 @@ struct Conv3x3Params {
   int prod_ct;
   int pair_dates;  // 1: iterate tiles as date pairs (needs G == 2)
   int out_bufs;    // 1 or 2 output staging buffers; 2 keeps the date-0 tile in smem for the date-1 product
+  unsigned long long mg_nt, mg_tx, mg_ty, mg_tb;  // fast_div magics for num_n_tiles, tiles_x, tiles_y, tiles_b
 };
 
 // warps [0, kEpiThreads/32): epilogue; then the TMA producer warp; then the MMA issuer warp LAST: the warp scheduler
@@ -59,9 +60,10 @@ constexpr int kHaloW = 10, kHaloH = 18;
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 23040
 constexpr int kHaloStage = 23552;                  // rounded up to 1024
 
-// one A stage: the halo tile (HALO), all nine 128px x 16ch tap boxes (Cin = 16), or one 128px x 64ch tap box
+// one A stage: the halo tile (HALO: 180 pixels x CK channels, rounded up to 1 KB), all nine 128px x 16ch tap boxes
+// (Cin = 16 without halo), or one 128px x 64ch tap box
 __host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) {
-  return halo ? kHaloStage : (CK == 16 ? 9 * 128 * 16 * 2 : 128 * CK * 2);
+  return halo ? ((kHaloW * kHaloH * CK * 2 + 1023) / 1024) * 1024 : (CK == 16 ? 9 * 128 * 16 * 2 : 128 * CK * 2);
 }
 __host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
 __host__ __device__ constexpr int conv_misc_bytes(int N_TILE) {
@@ -100,6 +102,11 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
 struct TileCoord {
   int n0, x0, y0, b0, g;
 };
+// n / d for n * d < 2^40 as one 64-bit multiply: m = ceil(2^40 / d) (host).  Replaces MUFU.RCP division sequences in
+// the per-tile paths of all three warp roles.
+__device__ __forceinline__ int fast_div(int n, unsigned long long m) {
+  return (int)(((unsigned long long)(unsigned)n * m) >> 40);
+}
 __device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, int N_TILE) {
   TileCoord c;
   int g_pair = 0;
@@ -107,15 +114,18 @@ __device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, 
     g_pair = t & 1;
     t >>= 1;
   }
-  int nt = t % p.num_n_tiles;
-  int m = t / p.num_n_tiles;
+  int m = fast_div(t, p.mg_nt);
+  const int nt = t - m * p.num_n_tiles;
   c.n0 = nt * N_TILE;
-  int tx = m % p.tiles_x;
-  m /= p.tiles_x;
-  int ty = m % p.tiles_y;
-  m /= p.tiles_y;
-  int tb = m % p.tiles_b;
-  c.g = p.pair_dates ? g_pair : m / p.tiles_b;
+  int q = fast_div(m, p.mg_tx);
+  const int tx = m - q * p.tiles_x;
+  m = q;
+  q = fast_div(m, p.mg_ty);
+  const int ty = m - q * p.tiles_y;
+  m = q;
+  q = fast_div(m, p.mg_tb);
+  const int tb = m - q * p.tiles_b;
+  c.g = p.pair_dates ? g_pair : q;
   c.x0 = tx * 8;
   c.y0 = ty * p.bh;
   c.b0 = tb * p.bn;
@@ -138,16 +148,18 @@ template <int N_TILE, int CK, bool HALO, bool RES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const Conv3x3Params p) {
+  // tmY: output map with the PER-WARP store box (64 ch x 8 x min(bh,4) x 4/min(bh,4)): each epilogue warp stores its
+  // own 32 pixel rows, so the four warps never synchronise with each other in steady state
   static_assert(CK == 64 || CK == 16, "channel chunk is 64 (128B swizzle) or 16 (32B swizzle)");
-  static_assert(!HALO || CK == 64, "halo mode needs 128-byte pixel rows");
   static_assert(N_TILE == 64 || N_TILE == 128 || N_TILE == 256, "N tile");
   constexpr int A_BYTES = conv_a_stage_bytes(CK, HALO);
-  constexpr int A_TX = HALO ? kHaloBytes : 128 * CK * 2;
+  constexpr int A_TX = HALO ? kHaloW * kHaloH * CK * 2 : 128 * CK * 2;
   constexpr int B_BYTES = conv_b_stage_bytes(N_TILE, CK);
   constexpr int OUT_BYTES = 128 * N_TILE * 2;
   constexpr uint32_t LAYOUT = (CK == 64) ? kLayoutSw128 : kLayoutSw32;
   constexpr uint32_t ROW_BYTES = CK * 2;
-  constexpr uint32_t A_SBO = HALO ? kHaloW * 128 : 8 * ROW_BYTES;
+  constexpr uint32_t A_SBO = HALO ? kHaloW * ROW_BYTES : 8 * ROW_BYTES;   // 8-pixel group stride: one (halo) row
+  constexpr uint32_t PIX16 = ROW_BYTES >> 4;                              // one pixel in descriptor units
   constexpr uint32_t B_SBO = 8 * ROW_BYTES;
   constexpr int TMEM_COLS = 2 * N_TILE;
   constexpr int NCHUNK = N_TILE / 32;
@@ -313,14 +325,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int r = 0; r < 3; ++r) {
 #pragma unroll
                 for (int s_ = 0; s_ < 3; ++s_) {
-                  const uint32_t a_tap = a_row + (HALO ? s_ * 8 : s_ * (A_TX >> 4));
+                  const uint32_t a_tap = a_row + (HALO ? s_ * PIX16 : s_ * (A_TX >> 4));
 #pragma unroll
                   for (int k = 0; k < CK / 16; ++k) {
                     umma_bf16(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_row + s_ * B_STEP + 2 * k), idesc, accumulate);
                     accumulate = 1;
                   }
                 }
-                a_row += HALO ? kHaloW * 8 : 3 * (A_TX >> 4);
+                a_row += HALO ? kHaloW * PIX16 : 3 * (A_TX >> 4);
                 b_row += 3 * B_STEP;
               }
               umma_commit(empty_a(sa));
@@ -336,7 +348,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               rb.advance(p.b_stages);
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t a_tap = a_lo + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * 8 : tap * (A_TX >> 4));
+                const uint32_t a_tap = a_lo + (HALO ? ((tap / 3) * kHaloW + (tap % 3)) * PIX16 : tap * (A_TX >> 4));
                 const uint32_t b_lo = b_lo_base + sb * B_STEP;
 #pragma unroll
                 for (int k = 0; k < CK / 16; ++k) {
@@ -404,33 +416,42 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int px = m & 7;
     const int py = (m >> 3) % p.bh;
     const int pn = (m >> 3) / p.bh;
+    // this warp's 4 tile rows (32 pixels) as a TMA store box: rows [wy, wy + min(bh,4)) of images [wn, ...)
+    const int wn = (q * 4) / p.bh, wy = (q * 4) % p.bh;
+    const bool affine = p.scale != nullptr || p.shift != nullptr;
+    const bool relu = p.relu != 0;
+    const bool extras = p.stats_out || p.pool_out || p.prod_out || p.head_out;   // one branch for the common plain tile
     int cur_n0 = -1;
     uint32_t tile_it = 0;
+    bar_sync(1, kEpiThreads);   // stats / head constants visible; the ONLY CTA-wide epilogue barrier in steady state
     for (int t; tile_at(p, (int)tile_it, total_tiles, t); ++tile_it) {
       const TileCoord tc = decode_tile(p, t, N_TILE);
       const int acc = tile_it & 1;
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
       const bool valid = gx < p.W && gy < p.H && gb < p.B;
       if (tc.n0 != cur_n0) {
+        // (once per CTA when the grid is a multiple of the N tiles) the warps are not in lockstep: fence both sides
+        bar_sync(1, kEpiThreads);
         for (int i = etid; i < N_TILE; i += kEpiThreads) {
           ss[i] = p.scale ? p.scale[tc.n0 + i] : 1.f;
           ss[N_TILE + i] = p.shift ? p.shift[tc.n0 + i] : 0.f;
         }
         cur_n0 = tc.n0;
+        bar_sync(1, kEpiThreads);
       }
-      mbar_wait(tmem_full(acc), (tile_it >> 1) & 1);
-      tc_fence_after();
       // output staging: with two buffers the previous tile stays readable in smem (date-0 tile of a product pair)
       const int ob = p.out_bufs == 2 ? (int)(tile_it & 1) : 0;
       uint8_t* out_sm = sm + out_off + ob * OUT_BYTES;
       const uint8_t* prev_sm = sm + out_off + (ob ^ 1) * OUT_BYTES;
       const bool prod_tile = p.prod_out && tc.g == 1;
-      if (etid == 0) {
+      if (lane == 0) {   // this warp's own earlier stores
         if (p.out_bufs == 2) tma_store_wait_read<1>();           // the store issued two tiles ago has drained this buffer
-        else if (prod_tile) tma_store_wait_all<0>();             // single buffer: date-0 tile is re-read from L2
+        else if (prod_tile) tma_store_wait_all<0>();             // single buffer: date-0 rows are re-read from L2
         else tma_store_wait_read<0>();
       }
-      bar_sync(1, kEpiThreads);
+      mbar_wait(tmem_full(acc), (tile_it >> 1) & 1);
+      tc_fence_after();
+      __syncwarp();
 
       float head0 = 0.f, head1 = 0.f;
 #pragma unroll 1
@@ -438,23 +459,23 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
-        float v[32];
         uint32_t pk[16];
+        if (affine) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(ss + cc * 32 + j);
-          const float4 sh = *reinterpret_cast<const float4*>(ss + N_TILE + cc * 32 + j);
-          v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
-          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(ss + cc * 32 + j);
+            const float4 sh = *reinterpret_cast<const float4*>(ss + N_TILE + cc * 32 + j);
+            pk[j / 2] = pack_bf16x2(fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x), fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
+            pk[j / 2 + 1] = pack_bf16x2(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
+          }
+        } else {  // raw accumulator (training forward before BatchNorm, data gradient)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         }
-        if (p.relu) {
+        if (relu) {  // on the packed pair: relu(round(x)) == round(relu(x))
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < 16; ++j) pk[j] = bf16x2_max(pk[j], 0u);
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 
         // staging for the TMA store: sub-tile (cc/2) of 64 channels, row m, 16-byte chunk index XOR (m & 7)
         {
@@ -466,6 +487,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<uint4*>(row + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
         }
+        if (extras) {
         if (p.stats_out) {
           // moments of the values as stored (bf16-rounded), invalid (out-of-image) pixels contribute 0
           float s1[32], s2[32];
@@ -531,32 +553,31 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             head1 = fmaf(hi, hw[64 + cc * 32 + 2 * j + 1], head1);
           }
         }
+        }  // extras
       }
       // accumulator drained -> MMA may overwrite it
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(acc));
 
-      float* hx = ss + 2 * N_TILE + 136;   // head partial sums of chunk group 1, [128 rows][2]
-      if (kEpiGroups == 2 && p.head_out && eg == 1) hx[2 * m] = head0, hx[2 * m + 1] = head1;
-      fence_proxy_async_smem();
-      bar_sync(1, kEpiThreads);
-      if (p.head_out && eg == 0 && valid) {
+      if (p.head_out && valid) {
         const float* hb = ss + 2 * N_TILE + 128;
         const size_t img = (size_t)tc.g * p.B + gb;
         const size_t plane = (size_t)p.H * p.W;
-        if (kEpiGroups == 2) head0 += hx[2 * m], head1 += hx[2 * m + 1];
         p.head_out[(img * 2 + 0) * plane + (size_t)gy * p.W + gx] = head0 + hb[0];
         p.head_out[(img * 2 + 1) * plane + (size_t)gy * p.W + gx] = head1 + hb[1];
       }
-      if (etid == 0 && p.store_main) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && p.store_main) {
 #pragma unroll
         for (int j = 0; j < N_TILE / 64; ++j)
-          tma_store_5d(&tmY, base + out_off + ob * OUT_BYTES + j * 16384, tc.n0 + j * 64, tc.x0, tc.y0, tc.b0, tc.g);
+          tma_store_5d(&tmY, base + out_off + ob * OUT_BYTES + j * 16384 + q * 4096, tc.n0 + j * 64, tc.x0, tc.y0 + wy,
+                       tc.b0 + wn, tc.g);
         tma_store_commit();
       }
     }
-    if (etid == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
     if (p.stats_out) {
       bar_sync(1, kEpiThreads);
       float* dst = p.stats_out + (size_t)blockIdx.x * (2 * N_TILE * 2);

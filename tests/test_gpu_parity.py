@@ -55,7 +55,9 @@ CONV_CASES = [
     (1, 2, 32, 32, 128, 128, dict(halo=1)),
     (1, 2, 32, 32, 128, 256, dict(halo=1, n_tile=256)),
     (1, 2, 32, 32, 128, 256, dict(halo=0, n_tile=128)),
-    (2, 2, 32, 32, 13, 64, dict()),                    # 13-band stem, channels padded to 16
+    (2, 2, 32, 32, 13, 64, dict()),                    # 13-band stem, channels padded to 16 (halo box, 32B swizzle)
+    (2, 2, 32, 32, 13, 64, dict(halo=0)),              # 13-band stem, nine tap boxes per stage
+    (1, 3, 45, 45, 13, 64, dict(halo=1)),
     (2, 3, 8, 8, 64, 128, dict()),                     # small maps: tiles span several images
     (2, 5, 4, 4, 128, 128, dict()),
     (2, 5, 2, 2, 128, 128, dict()),
