@@ -34,7 +34,8 @@ int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
   pl->qck = d->Cb == 16 ? 16 : 64;
   p.m_tiles = (d->Ca + 127) / 128;
   p.n_chunks = d->Cb / pl->qck;
-  const int items = p.m_tiles * p.n_chunks * 3;
+  p.row_items = d->Ca == 64 ? 2 : 3;
+  const int items = p.m_tiles * p.n_chunks * p.row_items;
   int splits = d->splits;
   if (splits <= 0) {
     splits = (2 * di.sms + items - 1) / items;

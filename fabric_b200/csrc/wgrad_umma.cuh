@@ -7,10 +7,13 @@
 // ([pixel][64 channels], 128B swizzle) and the UMMA descriptors read them with the channel index as the fast M/N
 // dimension and 8-pixel groups as the K dimension -- no transpose pass anywhere.
 //
-// Work item = (128 P-channels, 64 Q-channels, filter row r, K split): three accumulators (filter columns s=0..2) of
-// 128 x 64 fp32 in TMEM.  The Q tile is loaded once per pixel tile WITH its horizontal halo (10 pixels per row, row
-// y0+r-1 chosen by the TMA coordinate), and the three filter columns are three descriptors into that buffer (start
-// address + s pixels, stride-byte-offset = 10 pixels), as in the forward HALO mode.
+// Work item = (two 64-channel P atoms, 64 Q-channels, K split): three accumulators (filter columns s=0..2) of
+// 128 x 64 fp32 in TMEM.  The Q tile is loaded once per pixel tile WITH its horizontal halo (10 pixels per row); the
+// three filter columns are three descriptors into that buffer (start address + s pixels, stride-byte-offset = 10
+// pixels), as in the forward HALO mode.  The filter ROW is applied to the P tile instead: its TMA row coordinate is
+// y0 + 1 - r (out-of-image rows are zero-filled).  With Ca >= 128 the two P atoms are channels [c0, c0+64) and
+// [c0+64, c0+128) of one filter row; with Ca == 64 they are the SAME 64 channels for two different filter rows
+// (rows 0 and 1; row 2 runs with an empty second atom), so the M = 128 MMA is 75 % instead of 50 % useful.
 // WIDE mode issues ONE N=192 MMA instead of three N=64 ones: the three 64-channel N atoms are the same buffer at
 // leading-byte-offset = 1 pixel (overlapping atoms), which halves the A-operand shared-memory reads.
 #pragma once
@@ -24,6 +27,7 @@ struct WgradParams {
   int bh, bn;   // pixel tile = bn images x bh rows x 8 columns (bh * bn == 16)
   int tiles_x, tiles_y, tiles_b;
   int m_tiles, n_chunks, splits;
+  int row_items;  // filter-row work items per (m_tile, n_chunk): 3 (Ca >= 128) or 2 (Ca == 64: rows {0,1} and {2})
   int tiles_total;  // pixel tiles = G * tiles_b * tiles_y * tiles_x
   int stages;
   float* ws;  // [splits][Ca][9][Cb] fp32 partial sums
@@ -60,10 +64,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
   int it = blockIdx.x;
   const int split = it % p.splits;
   it /= p.splits;
-  const int r = it % 3;
-  it /= 3;
+  const int ri = it % p.row_items;
+  it /= p.row_items;
   const int nc = it % p.n_chunks;
   const int mt = it / p.n_chunks;
+  // the two P atoms: (channel offset, filter row); row < 0 = empty atom
+  const bool ca64 = p.row_items == 2;
+  const int ra = ca64 ? (ri == 0 ? 0 : 2) : ri;
+  const int rb = ca64 ? (ri == 0 ? 1 : -1) : ri;
+  const int ca_a = mt * 128, ca_b = ca64 ? 0 : mt * 128 + 64;
   const int t_begin = (int)((long long)p.tiles_total * split / p.splits);
   const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
 
@@ -104,9 +113,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
       if (elect_one()) {
         const uint32_t dst = base + stage * kWgStage;
         mbar_arrive_expect_tx(full(stage), kWgStage);  // P: 2 x 16 KB, Q: 160 pixel slots
-        tma_load_5d(dst, &tmP, full(stage), mt * 128, x0, y0, b0, g);
-        tma_load_5d(dst + 16384, &tmP, full(stage), mt * 128 + 64, x0, y0, b0, g);  // beyond Ca: zero filled
-        tma_load_5d(dst + kWgPBytes, &tmQ, full(stage), nc * QCK, x0 - 1, y0 + r - 1, b0, g);
+        tma_load_5d(dst, &tmP, full(stage), ca_a, x0, y0 + 1 - ra, b0, g);
+        // empty atom: a channel coordinate beyond Ca makes the whole box out of bounds = zero filled
+        tma_load_5d(dst + 16384, &tmP, full(stage), rb < 0 ? p.Ca : ca_b, x0, y0 + 1 - (rb < 0 ? 0 : rb), b0, g);
+        tma_load_5d(dst + kWgPBytes, &tmQ, full(stage), nc * QCK, x0 - 1, y0, b0, g);
       }
       __syncwarp();
       if (++stage == p.stages) stage = 0, phase ^= 1;
@@ -153,7 +163,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     // epilogue: 128 rows (P channels) x 3 taps x 64 Q channels -> fp32 partial slab of this split
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int ca = mt * 128 + row;
+    // accumulator row -> (dW row, filter row)
+    const int r = row < 64 ? ra : rb;
+    const int ca = row < 64 ? ca_a + row : ca_b + (row - 64);
     if (t_end > t_begin) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -171,7 +183,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (ca < p.Ca) {
+        if (r >= 0 && ca < p.Ca) {
           float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)split * p.Ca + ca) * 9 + (r * 3 + s)) * p.Cb + nc * QCK + cc * 32);
 #pragma unroll
           for (int i = 0; i < (NQ < 32 ? NQ : 32) / 4; ++i)
