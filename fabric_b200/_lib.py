@@ -57,7 +57,7 @@ SIGNATURES = {
     "fabric_b200_build_up_input": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_outconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_bn_finalize": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
-    "fabric_b200_bn_apply_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_apply_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_seg_loss_ws_floats": (_i64, [_i, _i, _i]),
     "fabric_b200_seg_loss_fwd_bwd": (_i, [_i, _f, _f, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fabric_b200_outconv_bwd_ws_floats": (_i64, [_i]),

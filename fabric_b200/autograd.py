@@ -17,8 +17,9 @@ KEEP_SAVED = False   # tests: keep the stored forward tensors of the last traini
 LAST_SAVED = None
 
 
-def _dc_forward(dc, x5, pool):
-    """double_conv in training mode.  Returns (a2, pooled, saved)."""
+def _dc_forward(dc, x5, pool, prod_out=None):
+    """double_conv in training mode.  Returns (a2, pooled, saved).  ``prod_out``: decoder input whose skip half
+    receives relu(a2[date 1] * a2[date 0]) from the BN-apply kernel."""
     c1, b1, c2, b2 = dc.conv[0], dc.conv[1], dc.conv[3], dc.conv[4]
     g, b, h, w, _ = x5.shape
     n = b * h * w
@@ -27,7 +28,7 @@ def _dc_forward(dc, x5, pool):
     a1, _ = ops.bn_apply_relu(r1["y"], s1[0], s1[1])
     r2 = ops.conv3x3(a1, dc._packed(3), dc.out_ch, stats=True, tune=dc.tune2)
     s2 = ops.bn_finalize(r2["stats"], b2, c2.bias, n, g)
-    a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool)
+    a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out)
     saved = dict(x=x5, z1=r1["y"], a1=a1, z2=r2["y"], a2=a2, s1=s1, s2=s2)
     return a2, pooled, saved
 
@@ -58,19 +59,25 @@ class _BiDateNetTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x_d1, x_d2, *params):
         x5 = model.pack_pair(x_d1, x_d2)
+        _, b, h, w, _ = x5.shape
+        dev = x5.device
+
+        def cat(level, cs, cl):     # decoder input; the skip half (relu(d2*d1)) is written by the encoder's BN-apply kernel
+            return torch.empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
+        cat4, cat3, cat2, cat1 = cat(0, 64, 64), cat(1, 128, 128), cat(2, 256, 256), cat(3, 512, 512)
         sv = {}
-        e1, p1, sv["inc"] = _dc_forward(model.inc.conv, x5, True)                 # bidate_model.py:23,29
-        e2, p2, sv["down1"] = _dc_forward(model.down1.mpconv[1], p1, True)        # :24,30
-        e3, p3, sv["down2"] = _dc_forward(model.down2.mpconv[1], p2, True)        # :25,31
-        e4, p4, sv["down3"] = _dc_forward(model.down3.mpconv[1], p3, True)        # :26,32
-        e5, _, sv["down4"] = _dc_forward(model.down4.mpconv[1], p4, False)        # :27,33
-        cat1 = ops.build_up_input(e4, e5)                                         # :35
+        e1, p1, sv["inc"] = _dc_forward(model.inc.conv, x5, True, cat4)                 # bidate_model.py:23,29 (+:38 skip)
+        e2, p2, sv["down1"] = _dc_forward(model.down1.mpconv[1], p1, True, cat3)        # :24,30 (+:37)
+        e3, p3, sv["down2"] = _dc_forward(model.down2.mpconv[1], p2, True, cat2)        # :25,31 (+:36)
+        e4, p4, sv["down3"] = _dc_forward(model.down3.mpconv[1], p3, True, cat1)        # :26,32 (+:35)
+        e5, _, sv["down4"] = _dc_forward(model.down4.mpconv[1], p4, False)              # :27,33
+        ops.build_up_input(None, e5, out=cat1)                                          # :35 upsampled half
         u1, _, sv["up1"] = _dc_forward(model.up1.conv, cat1, False)
-        cat2 = ops.build_up_input(e3, u1)                                         # :36
+        ops.build_up_input(None, u1, out=cat2)                                          # :36
         u2, _, sv["up2"] = _dc_forward(model.up2.conv, cat2, False)
-        cat3 = ops.build_up_input(e2, u2)                                         # :37
+        ops.build_up_input(None, u2, out=cat3)                                          # :37
         u3, _, sv["up3"] = _dc_forward(model.up3.conv, cat3, False)
-        cat4 = ops.build_up_input(e1, u3)                                         # :38
+        ops.build_up_input(None, u3, out=cat4)                                          # :38
         u4, _, sv["up4"] = _dc_forward(model.up4.conv, cat4, False)
         logits = ops.outconv(u4, model.outc.conv.weight, model.outc.conv.bias)   # :39
         ctx.model, ctx.sv, ctx.params = model, sv, params

@@ -61,47 +61,68 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid, in
   }
 }
 
-// a = relu(z * scale_g + shift_g) (+ 2x2 max pool).  One thread = 8 channels of one 2x2 pixel quad; 32-bit indexing.
-__global__ void __launch_bounds__(256, 4) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+// a = relu(z * scale_g + shift_g) (+ 2x2 max pool) (+ relu(a_d2 * a_d1) into the decoder input).  One thread = 8 channels
+// of one 2x2 pixel quad, for BOTH date groups when the product is fused; 32-bit indexing.
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, uint4* __restrict__ a,
-                                                          uint4* __restrict__ pool, int G, int B, int H, int W, int C) {
+                                                          uint4* __restrict__ pool, uint4* __restrict__ prod, int prod_c8,
+                                                          int G, int B, int H, int W, int C) {
   const uint32_t C8 = C >> 3, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
-  const uint32_t total = (uint32_t)G * B * Hq * Wq * C8;
+  const uint32_t GB = prod ? (uint32_t)B : (uint32_t)G * B;   // with the product fused a thread walks both date groups
+  const uint32_t total = GB * Hq * Wq * C8;
+  const uint32_t ngroups = prod ? 2u : 1u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint32_t c8 = i % C8;
     uint32_t q = i / C8;
     const uint32_t qx = q % Wq;
     q /= Wq;
     const uint32_t qy = q % Hq;
-    q /= Hq;  // = g * B + b
-    const uint32_t g = q >= (uint32_t)B ? 1u : 0u;
-    float sc[8], sh[8], m[8];
-    ld8f(scale + g * C + c8 * 8, sc);
-    ld8f(shift + g * C + c8 * 8, sh);
+    q /= Hq;  // = g * B + b (or b with the product fused)
+    uint4 first[4];
+    for (uint32_t gi = 0; gi < ngroups; ++gi) {
+      const uint32_t img = q + gi * B;                       // image index in [0, G*B)
+      const uint32_t g = img >= (uint32_t)B ? 1u : 0u;
+      float sc[8], sh[8], m[8];
+      ld8f(scale + g * C + c8 * 8, sc);
+      ld8f(shift + g * C + c8 * 8, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = 0.f;  // post-ReLU values are >= 0
-    uint4 zin[4];
-    bool ok[4];
+      for (int j = 0; j < 8; ++j) m[j] = 0.f;  // post-ReLU values are >= 0
+      uint4 zin[4];
+      bool ok[4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-      ok[d] = y < (uint32_t)H && x < (uint32_t)W;
-      if (ok[d]) zin[d] = __ldg(z + (size_t)((q * H + y) * W + x) * C8 + c8);
-    }
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      if (!ok[d]) continue;
-      const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-      float f[8];
-      unpack8(zin[d], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-        m[j] = fmaxf(m[j], f[j]);
+      for (int d = 0; d < 4; ++d) {
+        const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+        ok[d] = y < (uint32_t)H && x < (uint32_t)W;
+        if (ok[d]) zin[d] = __ldg(z + (size_t)((img * H + y) * W + x) * C8 + c8);
       }
-      a[(size_t)((q * H + y) * W + x) * C8 + c8] = pack8(f);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (!ok[d]) continue;
+        const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+        float f[8];
+        unpack8(zin[d], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+          m[j] = fmaxf(m[j], f[j]);
+        }
+        const uint4 av = pack8(f);
+        a[(size_t)((img * H + y) * W + x) * C8 + c8] = av;
+        if (prod) {
+          if (gi == 0) {
+            first[d] = av;
+          } else {   // relu(a_d2 * a_d1) on the stored (bf16) activations, bidate_model.py:35-38
+            float f0[8], f1[8], r[8];
+            unpack8(first[d], f0);
+            unpack8(av, f1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fmaxf(f0[j] * f1[j], 0.f);
+            prod[(size_t)((q * H + y) * W + x) * prod_c8 + c8] = pack8(r);
+          }
+        }
+      }
+      if (pool && qy < Hp && qx < Wp) pool[(size_t)((img * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
     }
-    if (pool && qy < Hp && qx < Wp) pool[(size_t)((q * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
   }
 }
 
@@ -591,18 +612,19 @@ int fabric_b200_bn_finalize(const float* stats_ws, int grid, int n_tile, int C, 
   return FB_OK;
 }
 
-int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, int G, int B,
-                              int H, int W, int C, void* stream) {
+int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, void* prod_out,
+                              int prod_channels, int G, int B, int H, int W, int C, void* stream) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   if (!z || !scale || !shift || !a) return fail(FB_ERR_ARG, "null pointer");
   if (C % 8) return fail(FB_ERR_SHAPE, "C must be a multiple of 8");
   if ((double)G * B * H * W * C / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
-  const size_t n = (size_t)G * B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  if (prod_out && (G != 2 || prod_channels < C || prod_channels % 8)) return fail(FB_ERR_SHAPE, "product fusion needs G == 2 and prod_channels >= C");
+  const size_t n = (size_t)(prod_out ? 1 : G) * B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   bn_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(pool_out), G, B,
-      H, W, C);
+      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(pool_out),
+      reinterpret_cast<uint4*>(prod_out), prod_channels / 8, G, B, H, W, C);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

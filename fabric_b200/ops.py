@@ -230,12 +230,19 @@ def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_
     return out
 
 
-def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, pool: bool = False):
+def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, pool: bool = False,
+                  prod_out: Optional[torch.Tensor] = None):
+    """a = relu(z*scale[g]+shift[g]) (+ MaxPool2d(2) copy) (+ relu(a[1]*a[0]) into prod_out[..., :C], the skip half of the
+    decoder input [1,B,H,W,Ct])."""
     g, b, h, w, c = z5.shape
     a = torch.empty_like(z5)
     pl = torch.empty((g, b, h // 2, w // 2, c), dtype=torch.bfloat16, device=z5.device) if pool else None
-    check(_lib.load().fabric_b200_bn_apply_relu(_p(z5), _p(scale), _p(shift), _p(a), _p(pl), g, b, h, w, c, _stream()),
-          "bn_apply_relu")
+    pc = 0
+    if prod_out is not None:
+        assert g == 2 and prod_out.shape[:4] == (1, b, h, w)
+        pc = prod_out.shape[4]
+    check(_lib.load().fabric_b200_bn_apply_relu(_p(z5), _p(scale), _p(shift), _p(a), _p(pl), _p(prod_out), pc, g, b, h, w, c,
+                                                _stream()), "bn_apply_relu")
     _count()
     return a, pl
 

@@ -125,9 +125,10 @@ int fabric_b200_bn_finalize(const float* stats_ws, int grid, int n_tile, int C, 
                             const float* conv_bias, const float* gamma, const float* beta, float* running_mean,
                             float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* scale,
                             float* shift, float* mean, float* invstd, void* stream);
-/* a = relu(z*scale[g] + shift[g]) bf16 NHWC5, optional fused MaxPool2d(2) copy */
-int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, int G, int B,
-                              int H, int W, int C, void* stream);
+/* a = relu(z*scale[g] + shift[g]) bf16 NHWC5, optional fused MaxPool2d(2) copy, optional fused
+ * relu(a[date 1] * a[date 0]) written into channels [0, C) of prod_out [B][H][W][prod_channels] (G == 2) */
+int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, void* prod_out,
+                              int prod_channels, int G, int B, int H, int W, int C, void* stream);
 
 /* ---- training: losses (utils/metrics.py) --------------------------------------------------------------------- */
 

@@ -346,3 +346,20 @@ def test_fused_sgd_step_equals_torch_sgd(cuda):
     for k in outs[0][0]:
         assert torch.equal(outs[0][0][k], outs[1][0][k]), k
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("H,W,C", [(32, 32, 64), (45, 45, 128), (5, 5, 256)])
+def test_bn_apply_fused_date_product(cuda, H, W, C):
+    """relu(a[date 1] * a[date 0]) (reference bidate_model.py:35-38) fused into the training-mode BN-apply kernel"""
+    from fabric_b200 import ops
+    torch.manual_seed(21)
+    B = 3
+    z = torch.randn(2, B, H, W, C, device=cuda).bfloat16()
+    scale = (0.5 + torch.rand(2, C, device=cuda)).contiguous()
+    shift = (0.3 * torch.randn(2, C, device=cuda)).contiguous()
+    cat = torch.full((1, B, H, W, C + 64), 3.0, device=cuda, dtype=torch.bfloat16)
+    a_plain, p_plain = ops.bn_apply_relu(z, scale, shift, pool=True)
+    a, p = ops.bn_apply_relu(z, scale, shift, pool=True, prod_out=cat)
+    assert torch.equal(a, a_plain) and torch.equal(p, p_plain)
+    assert torch.equal(cat[0, ..., :C], torch.relu(a[0].float() * a[1].float()).bfloat16())
+    assert bool((cat[0, ..., C:] == 3.0).all())
