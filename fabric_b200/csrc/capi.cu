@@ -9,7 +9,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------ conv planning
 struct ConvPlan {
   fb::Conv3x3Params p;
-  int n_tile, ck, halo, grid, smem;
+  int n_tile, ck, halo, grid, smem, ctas;
 };
 
 int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
@@ -51,29 +51,40 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (halo < 0) halo = halo_ok ? 1 : 0;
   if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs H > 8");
 
-  // in date-pair mode the persistent loop runs over units (spatial tile x N tile), each = 2 tiles
-  const long long total = (long long)p.num_m_tiles * p.num_n_tiles / (d->prod_out ? 2 : 1);
-  int grid = d->tune.grid > 0 ? d->tune.grid : di.sms;
-  if (grid > total) grid = (int)total;
-  else grid = (grid / p.num_n_tiles) * p.num_n_tiles;  // each CTA keeps one N tile for its whole life
-  if (grid < 1) grid = (int)(total < p.num_n_tiles ? total : p.num_n_tiles);
-  const bool n_const = (grid % p.num_n_tiles == 0) || grid == total;
-  if (d->stats_ws && grid % p.num_n_tiles != 0 && grid != total)
+  // CTA pairs (cta_group::2): two adjacent M tiles share one M = 256 MMA and each CTA stages half of the weight rows.
+  // Needs an even number of M tiles per date-pair unit and room for at least one pair per N tile.
+  const int m_units = p.num_m_tiles / (d->prod_out ? 2 : 1);   // M tiles the persistent loop enumerates
+  int ctas = d->tune.ctas;
+  const bool pair_ok = (m_units % 2 == 0) && di.sms >= 2 * p.num_n_tiles;
+  if (ctas == 0) ctas = pair_ok ? 2 : 1;
+  if (ctas != 1 && ctas != 2) return fail(FB_ERR_ARG, "tune.ctas must be 0 (auto), 1 or 2");
+  if (ctas == 2 && !pair_ok) return fail(FB_ERR_SHAPE, "CTA pairs need an even number of M tiles (%d)", m_units);
+  // in date-pair mode the persistent loop runs over units (spatial tile x N tile), each visited for both dates;
+  // slots = CTAs or CTA pairs
+  const long long total = (long long)(m_units / ctas) * p.num_n_tiles;
+  p.total_units = (int)total;
+  int slots = (d->tune.grid > 0 ? d->tune.grid : di.sms) / ctas;
+  if (slots > total) slots = (int)total;
+  else slots = (slots / p.num_n_tiles) * p.num_n_tiles;  // each CTA keeps one N tile for its whole life
+  if (slots < 1) slots = (int)(total < p.num_n_tiles ? total : p.num_n_tiles);
+  const int grid = slots * ctas;
+  const bool n_const = (slots % p.num_n_tiles == 0) || slots == total;
+  if (d->stats_ws && slots % p.num_n_tiles != 0 && slots != total)
     return fail(FB_ERR_SHAPE, "stats need a grid that is a multiple of the N tiles");
 
   const int a_bytes = fb::conv_a_stage_bytes(ck, halo);
-  const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck);
+  const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck) / ctas;
   // product fusion keeps the date-0 tile in a second staging buffer when the N tile is small enough
   // (measured: a second buffer does NOT help ordinary tiles -- the previous store has long drained -- and costs the
   //  128->64 layers their resident weights, so it is used for product pairs only)
   const int out_bufs = (d->prod_out && n_tile <= 128) ? 2 : 1;
-  const int fixed = out_bufs * 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile) + 1024;
+  const int fixed = out_bufs * 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr) + 1024;
   const int avail = di.smem_optin - fixed;
   const int kblocks = 9 * p.kchunks;
   int b_res = d->tune.b_resident;
-  const bool res_fits = n_const && (grid % p.num_n_tiles == 0 || p.num_n_tiles == 1 || grid == total) &&
-                        (long long)kblocks * b_bytes + 2 * a_bytes <= avail && kblocks <= 18;
-  if (b_res < 0) b_res = (res_fits && grid < total) ? 1 : 0;
+  const bool res_fits = n_const && (slots % p.num_n_tiles == 0 || p.num_n_tiles == 1 || slots == total) &&
+                        (long long)kblocks * b_bytes + 2 * a_bytes <= avail && kblocks <= 36;
+  if (b_res < 0) b_res = (res_fits && slots < total) ? 1 : 0;
   if (ck == 16) b_res = 1;  // the 13-band stem keeps its 18 KB of weights resident and stages all nine taps at once
   if (b_res && !res_fits) return fail(FB_ERR_SHAPE, "resident weights do not fit (%d k-blocks of %d B)", kblocks, b_bytes);
   // a CTA whose tiles alternate N tiles cannot keep weights resident; with grid == total each CTA has one tile
@@ -92,7 +103,7 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
     if (a_st <= 0) a_st = s;
     if (b_st <= 0) b_st = s;
   }
-  if (a_st < 1 || b_st < 1 || a_st > 8 || b_st > 18) return fail(FB_ERR_SHAPE, "bad stage counts %d/%d", a_st, b_st);
+  if (a_st < 1 || b_st < 1 || a_st > 8 || b_st > 36) return fail(FB_ERR_SHAPE, "bad stage counts %d/%d", a_st, b_st);
   const long long smem = (long long)a_st * a_bytes + (long long)b_st * b_bytes + fixed;
   if (smem > di.smem_optin) return fail(FB_ERR_SHAPE, "shared memory %lld > %d", smem, di.smem_optin);
   p.a_stages = a_st, p.b_stages = b_st, p.b_resident = b_res;
@@ -107,15 +118,21 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   p.mg_nt = magic(p.num_n_tiles), p.mg_tx = magic(p.tiles_x), p.mg_ty = magic(p.tiles_y), p.mg_tb = magic(p.tiles_b);
   if ((double)p.num_m_tiles * p.num_n_tiles * 65536.0 >= 1.0e12) return fail(FB_ERR_SHAPE, "too many tiles");
   p.out_bufs = out_bufs;
-  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem;
+  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas;
   return FB_OK;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES>
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS>
 int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY, cudaStream_t st) {
-  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES>;
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-  k<<<pl.grid, fb::kConvThreads, pl.smem, st>>>(tA, tB, tY, pl.p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid), cfg.blockDim = dim3(fb::kConvThreads), cfg.dynamicSmemBytes = pl.smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;   // a CTA pair = one cluster of 2 on one TPC
+  at[0].val.clusterDim.x = CTAS, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  FB_CUDA(cudaLaunchKernelEx(&cfg, k, tA, tB, tY, pl.p));
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -364,7 +381,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   if (pl.halo) rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, pl.ck, fb::kHaloW, fb::kHaloH, 1, sw_a);
   else rc = make_tmap_act(&tA, d->x, p.Cin, p.W, p.H, p.B, p.G, pl.ck, 8, p.bh, p.bn, sw_a);
   if (rc) return rc;
-  rc = make_tmap_2d(&tB, d->w, p.Cout, 9LL * p.Cin, pl.n_tile, pl.ck, sw_a);
+  rc = make_tmap_2d(&tB, d->w, p.Cout, 9LL * p.Cin, pl.n_tile / pl.ctas, pl.ck, sw_a);   // a CTA of a pair loads half the rows
   if (rc) return rc;
   // y may be absent (head-only): the map is still needed as a kernel argument, point it at x's storage
   // store box = one epilogue warp's 32 pixel rows
@@ -374,8 +391,11 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool res = p.b_resident != 0;
-#define FB_DISPATCH(NT, CK, HL, RS) \
-  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) return launch_conv<NT, CK, HL, RS>(pl, tA, tB, tY, st);
+#define FB_DISPATCH(NT, CK, HL, RS)                                                                     \
+  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) {                            \
+    if (pl.ctas == 2) return launch_conv<NT, CK, HL, RS, 2>(pl, tA, tB, tY, st);                        \
+    return launch_conv<NT, CK, HL, RS, 1>(pl, tA, tB, tY, st);                                          \
+  }
   FB_DISPATCH(64, 16, false, true)
   FB_DISPATCH(64, 16, true, true)
   FB_DISPATCH(64, 64, false, false)

@@ -27,6 +27,7 @@ struct Conv3x3Params {
   int bh, bn;  // tile = bn images x bh rows x 8 columns, bh * bn == 16
   int tiles_x, tiles_y, tiles_b;
   int num_m_tiles, num_n_tiles;
+  int total_units;  // persistent work items: (M tile [pair with CTAS = 2]) x N tile (x both dates in pair_dates mode)
   int kchunks;  // Cin / CK
   int a_stages, b_stages;
   int b_resident;  // weights for this CTA's N tile stay in smem for the whole kernel
@@ -66,9 +67,11 @@ __host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) {
   return halo ? ((kHaloW * kHaloH * CK * 2 + 1023) / 1024) * 1024 : (CK == 16 ? 9 * 128 * 16 * 2 : 128 * CK * 2);
 }
 __host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
-__host__ __device__ constexpr int conv_misc_bytes(int N_TILE) {
-  // scale/shift + head weights (+ head exchange with two epilogue groups), stats slabs, barriers + tmem pointer
-  return (2 * N_TILE + 136 + (kEpiGroups == 2 ? 256 : 0)) * 4 + 4 * 2 * N_TILE * 2 * 4 + 1024;
+__host__ __device__ constexpr int conv_stats_bytes(int N_TILE) { return 4 * 2 * N_TILE * 2 * 4; }
+__host__ __device__ constexpr int conv_misc_bytes(int N_TILE, bool stats) {
+  // scale/shift + head weights (+ head exchange with two epilogue groups), stats slabs (only when BN moments are
+  // requested), barriers + tmem pointer
+  return (2 * N_TILE + 136 + (kEpiGroups == 2 ? 256 : 0)) * 4 + (stats ? conv_stats_bytes(N_TILE) : 0) + 1024;
 }
 
 // column sums over the 32 lanes of a warp: returns sum_lanes v[lane_id]  (31 shuffles instead of 160)
@@ -107,15 +110,25 @@ struct TileCoord {
 __device__ __forceinline__ int fast_div(int n, unsigned long long m) {
   return (int)(((unsigned long long)(unsigned)n * m) >> 40);
 }
-__device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, int N_TILE) {
-  TileCoord c;
-  int g_pair = 0;
-  if (p.pair_dates) {  // t enumerates (unit, date) with the date fastest
-    g_pair = t & 1;
-    t >>= 1;
+// Persistent tile iteration shared by the three warp roles.  A slot is a CTA (CTAS = 1) or a CTA pair (CTAS = 2); slot s
+// owns units s, s + nslots, ...; a unit = (M tile or pair of adjacent M tiles) x N tile.  In pair_dates mode every unit
+// is visited twice back to back: date 0, then date 1 (product fusion).  With CTAS = 2 the two CTAs take M tiles
+// 2k + rank of the same unit.
+template <int CTAS>
+__device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int N_TILE, int rank, TileCoord& c) {
+  const int nslots = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int slot = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  int unit, date = 0;
+  if (p.pair_dates) {
+    unit = slot + (it >> 1) * nslots;
+    date = it & 1;
+  } else {
+    unit = slot + it * nslots;
   }
-  int m = fast_div(t, p.mg_nt);
-  const int nt = t - m * p.num_n_tiles;
+  if (unit >= p.total_units) return false;
+  int m = fast_div(unit, p.mg_nt);
+  const int nt = unit - m * p.num_n_tiles;
+  if (CTAS == 2) m = 2 * m + rank;
   c.n0 = nt * N_TILE;
   int q = fast_div(m, p.mg_tx);
   const int tx = m - q * p.tiles_x;
@@ -125,26 +138,14 @@ __device__ __forceinline__ TileCoord decode_tile(const Conv3x3Params& p, int t, 
   m = q;
   q = fast_div(m, p.mg_tb);
   const int tb = m - q * p.tiles_b;
-  c.g = p.pair_dates ? g_pair : q;
+  c.g = p.pair_dates ? date : q;
   c.x0 = tx * 8;
   c.y0 = ty * p.bh;
   c.b0 = tb * p.bn;
-  return c;
+  return true;
 }
 
-// Persistent tile iteration shared by the three warp roles.  Plain mode: tile = block + it * grid.  Pair mode: the CTA
-// owns units block + k * grid and visits (unit, date 0), (unit, date 1) back to back.
-__device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int total_tiles, int& t) {
-  if (p.pair_dates) {
-    const int unit = blockIdx.x + (it >> 1) * gridDim.x;
-    t = unit * 2 + (it & 1);
-  } else {
-    t = blockIdx.x + it * gridDim.x;
-  }
-  return t < total_tiles;
-}
-
-template <int N_TILE, int CK, bool HALO, bool RES>
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const Conv3x3Params p) {
@@ -152,9 +153,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // own 32 pixel rows, so the four warps never synchronise with each other in steady state
   static_assert(CK == 64 || CK == 16, "channel chunk is 64 (128B swizzle) or 16 (32B swizzle)");
   static_assert(N_TILE == 64 || N_TILE == 128 || N_TILE == 256, "N tile");
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair (cta_group::2) per tile row");
   constexpr int A_BYTES = conv_a_stage_bytes(CK, HALO);
   constexpr int A_TX = HALO ? kHaloW * kHaloH * CK * 2 : 128 * CK * 2;
-  constexpr int B_BYTES = conv_b_stage_bytes(N_TILE, CK);
+  constexpr int B_BYTES = conv_b_stage_bytes(N_TILE, CK) / CTAS;   // a CTA of a pair stages half of the weight rows
   constexpr int OUT_BYTES = 128 * N_TILE * 2;
   constexpr uint32_t LAYOUT = (CK == 64) ? kLayoutSw128 : kLayoutSw32;
   constexpr uint32_t ROW_BYTES = CK * 2;
@@ -174,7 +176,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t out_off = b_off + p.b_stages * B_BYTES;
   const uint32_t ss_off = out_off + p.out_bufs * OUT_BYTES;
   const uint32_t st_off = ss_off + (2 * N_TILE + 136 + (kEpiGroups == 2 ? 256 : 0)) * 4;
-  const uint32_t bar_off = st_off + 4 * 2 * N_TILE * 2 * 4;
+  const uint32_t bar_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
 
   float* ss = reinterpret_cast<float*>(sm + ss_off);       // [0,N) scale, [N,2N) shift, [2N,2N+128) head w, +128.. head b
   float* stats = reinterpret_cast<float*>(sm + st_off);    // [4 warps][2 groups][N_TILE][2]
@@ -190,7 +192,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  // barriers the MMA issuer waits on live in the leader CTA (rank 0); the peer arms / completes them remotely
+  const uint32_t lead_delta = CTAS == 2 ? mapa_shared(bars, 0) - bars : 0u;
+  auto on_leader = [&](uint32_t bar) { return bar + lead_delta; };
 
   constexpr int kProducerWarp = kEpiThreads / 32, kMmaWarp = kProducerWarp + 1;
   if (warp == kProducerWarp && lane == 0) {
@@ -199,8 +204,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmY);
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(base + bar_off + 1000, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem2_alloc(base + bar_off + 1000, TMEM_COLS);
+      tmem2_relinquish();
+    } else {
+      tmem_alloc(base + bar_off + 1000, TMEM_COLS);
+      tmem_relinquish();
+    }
     if (lane == 0) {
       for (int s = 0; s < p.a_stages; ++s) {
         mbar_init(full_a(s), 1);
@@ -212,13 +222,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tmem_full(s), 1);
-        mbar_init(tmem_empty(s), kEpiThreads / 32);
+        mbar_init(tmem_empty(s), CTAS * (kEpiThreads / 32));
       }
       fence_mbar_init();
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -239,8 +250,22 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================================================ TMA producer (whole warp loops, one lane issues)
     Ring ra, rb;
     bool first_tile = true;
-    for (int it = 0, t; tile_at(p, it, total_tiles, t); ++it) {
-      const TileCoord tc = decode_tile(p, t, N_TILE);
+    // CTA pair: the leader arms its own barrier for the bytes of BOTH CTAs; the peer only issues its loads, whose
+    // complete_tx lands on the leader's barrier (a transiently negative tx-count is fine: the phase cannot complete
+    // before the leader's arrival).  No remote arrive on the load path.
+    auto arm = [&](uint32_t bar, uint32_t bytes) {
+      if (rank == 0) mbar_arrive_expect_tx(bar, CTAS * bytes);
+    };
+    auto load_a = [&](uint32_t dst, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+      if (CTAS == 2) tma2_load_5d(dst, &tmA, on_leader(bar), c0, c1, c2, c3, c4);
+      else tma_load_5d(dst, &tmA, bar, c0, c1, c2, c3, c4);
+    };
+    auto load_b = [&](uint32_t dst, uint32_t bar, int c0, int c1) {
+      if (CTAS == 2) tma2_load_2d(dst, &tmB, on_leader(bar), c0, c1 + rank * (N_TILE / 2));
+      else tma_load_2d(dst, &tmB, bar, c0, c1);
+    };
+    TileCoord tc;
+    for (int it = 0; tile_at<CTAS>(p, it, N_TILE, rank, tc); ++it) {
       for (int c = 0; c < p.kchunks; ++c) {
         for (int tap = 0; tap < 9; ++tap) {
           if (tap % TAPS_PER_A == 0) {
@@ -248,17 +273,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (elect_one()) {
               const uint32_t dst = base + a_off + ra.stage * A_BYTES;
               if (HALO) {
-                mbar_arrive_expect_tx(full_a(ra.stage), A_TX);
-                tma_load_5d(dst, &tmA, full_a(ra.stage), c * CK, tc.x0 - 1, tc.y0 - 1, tc.b0, tc.g);
+                arm(full_a(ra.stage), A_TX);
+                load_a(dst, full_a(ra.stage), c * CK, tc.x0 - 1, tc.y0 - 1, tc.b0, tc.g);
               } else if (CK == 16) {
-                mbar_arrive_expect_tx(full_a(ra.stage), 9 * A_TX);
+                arm(full_a(ra.stage), 9 * A_TX);
 #pragma unroll
                 for (int tt = 0; tt < 9; ++tt)
-                  tma_load_5d(dst + tt * A_TX, &tmA, full_a(ra.stage), c * CK, tc.x0 + (tt % 3) - 1, tc.y0 + (tt / 3) - 1,
-                              tc.b0, tc.g);
+                  load_a(dst + tt * A_TX, full_a(ra.stage), c * CK, tc.x0 + (tt % 3) - 1, tc.y0 + (tt / 3) - 1, tc.b0, tc.g);
               } else {
-                mbar_arrive_expect_tx(full_a(ra.stage), A_TX);
-                tma_load_5d(dst, &tmA, full_a(ra.stage), c * CK, tc.x0 + (tap % 3) - 1, tc.y0 + (tap / 3) - 1, tc.b0, tc.g);
+                arm(full_a(ra.stage), A_TX);
+                load_a(dst, full_a(ra.stage), c * CK, tc.x0 + (tap % 3) - 1, tc.y0 + (tap / 3) - 1, tc.b0, tc.g);
               }
             }
             __syncwarp();
@@ -267,16 +291,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (!RES) {
             mbar_wait(empty_b(rb.stage), rb.phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(full_b(rb.stage), B_BYTES);
-              tma_load_2d(base + b_off + rb.stage * B_BYTES, &tmB, full_b(rb.stage), tap * p.Cin + c * CK, tc.n0);
+              arm(full_b(rb.stage), B_BYTES);
+              load_b(base + b_off + rb.stage * B_BYTES, full_b(rb.stage), tap * p.Cin + c * CK, tc.n0);
             }
             __syncwarp();
             rb.advance(p.b_stages);
           } else if (first_tile) {  // RES: the CTA's weight slab is loaded once
             if (elect_one()) {
               const int s = c * 9 + tap;
-              mbar_arrive_expect_tx(full_b(s), B_BYTES);
-              tma_load_2d(base + b_off + s * B_BYTES, &tmB, full_b(s), tap * p.Cin + c * CK, tc.n0);
+              arm(full_b(s), B_BYTES);
+              load_b(base + b_off + s * B_BYTES, full_b(s), tap * p.Cin + c * CK, tc.n0);
             }
             __syncwarp();
           }
@@ -285,10 +309,19 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       first_tile = false;
     }
   } else if (warp == kMmaWarp) {
+    if (rank == 0) {   // a CTA pair is fed by the leader's MMA warp alone
     // ================================================================ MMA issuer (whole warp loops, one lane issues)
     // This warp's instruction stream is the critical path of the kernel (one thread feeds the tensor core), so the
     // loop is kept lean: taps fully unrolled with constant descriptor offsets, descriptors = base + small adds.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, N_TILE, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(128 * CTAS, N_TILE, 0, 0);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc_flag) {
+      if (CTAS == 2) umma2_bf16(d, ad, bd, idesc, acc_flag);
+      else umma_bf16(d, ad, bd, idesc, acc_flag);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (CTAS == 2) umma2_commit(bar);
+      else umma_commit(bar);
+    };
     constexpr uint64_t a_hi = umma_desc(0, 16, A_SBO, LAYOUT) & 0xFFFFFFFF00000000ull;
     constexpr uint64_t b_hi = umma_desc(0, 16, B_SBO, LAYOUT) & 0xFFFFFFFF00000000ull;
     constexpr uint32_t lo_fixed = static_cast<uint32_t>(umma_desc(0, 16, 0, 0) & 0xFFFFFFFFu);
@@ -297,7 +330,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint32_t A_STEP = A_BYTES >> 4, B_STEP = B_BYTES >> 4;
     Ring ra, rb;
     uint32_t tile_it = 0;
-    for (int t; tile_at(p, (int)tile_it, total_tiles, t); ++tile_it) {
+    TileCoord tc_unused;
+    for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, 0, tc_unused); ++tile_it) {
       const int acc = tile_it & 1;
       mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -328,15 +362,15 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   const uint32_t a_tap = a_row + (HALO ? s_ * PIX16 : s_ * (A_TX >> 4));
 #pragma unroll
                   for (int k = 0; k < CK / 16; ++k) {
-                    umma_bf16(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_row + s_ * B_STEP + 2 * k), idesc, accumulate);
+                    mma(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_row + s_ * B_STEP + 2 * k), accumulate);
                     accumulate = 1;
                   }
                 }
                 a_row += HALO ? kHaloW * PIX16 : 3 * (A_TX >> 4);
                 b_row += 3 * B_STEP;
               }
-              umma_commit(empty_a(sa));
-              if (last_chunk) umma_commit(tmem_full(acc));
+              commit(empty_a(sa));
+              if (last_chunk) commit(tmem_full(acc));
             }
             __syncwarp();
             accumulate = 1;
@@ -352,13 +386,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t b_lo = b_lo_base + sb * B_STEP;
 #pragma unroll
                 for (int k = 0; k < CK / 16; ++k) {
-                  umma_bf16(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_lo + 2 * k), idesc, accumulate);
+                  mma(d_tmem, a_hi | (a_tap + 2 * k), b_hi | (b_lo + 2 * k), accumulate);
                   accumulate = 1;
                 }
-                umma_commit(empty_b(sb));
+                commit(empty_b(sb));
                 if (tap == 8) {
-                  umma_commit(empty_a(sa));
-                  if (last_chunk) umma_commit(tmem_full(acc));
+                  commit(empty_a(sa));
+                  if (last_chunk) commit(tmem_full(acc));
                 }
               }
               __syncwarp();
@@ -387,12 +421,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint32_t b_lo = b_lo_base + sb * B_STEP;
 #pragma unroll
               for (int k = 0; k < CK / 16; ++k) {
-                umma_bf16(d_tmem, a_hi | (a_lo + 2 * k), b_hi | (b_lo + 2 * k), idesc, accumulate);
+                mma(d_tmem, a_hi | (a_lo + 2 * k), b_hi | (b_lo + 2 * k), accumulate);
                 accumulate = 1;
               }
-              if constexpr (!RES) umma_commit(empty_b(sb));
-              umma_commit(empty_a(sa));
-              if (last_chunk && tap == 8) umma_commit(tmem_full(acc));
+              if constexpr (!RES) commit(empty_b(sb));
+              commit(empty_a(sa));
+              if (last_chunk && tap == 8) commit(tmem_full(acc));
             }
             __syncwarp();
             accumulate = 1;
@@ -400,6 +434,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    }  // leader
   } else {
     // ================================================================ epilogue (kEpiThreads threads)
     // With kEpiGroups == 2 there are two warps per TMEM lane quarter: group eg takes every other 32-column chunk.
@@ -408,7 +443,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int m = q * 32 + lane;        // pixel row of the tile
     const int etid = threadIdx.x;       // epilogue warps come first
     float* my_stats = stats + q * (2 * N_TILE * 2);
-    for (int i = etid; i < 4 * 2 * N_TILE * 2; i += kEpiThreads) stats[i] = 0.f;
+    if (p.stats_out)   // (the slabs exist only then)
+      for (int i = etid; i < 4 * 2 * N_TILE * 2; i += kEpiThreads) stats[i] = 0.f;
     if (p.head_out) {
       for (int i = etid; i < 128; i += kEpiThreads) ss[2 * N_TILE + i] = p.head_w[i];
       if (etid < 2) ss[2 * N_TILE + 128 + etid] = p.head_b[etid];
@@ -424,8 +460,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int cur_n0 = -1;
     uint32_t tile_it = 0;
     bar_sync(1, kEpiThreads);   // stats / head constants visible; the ONLY CTA-wide epilogue barrier in steady state
-    for (int t; tile_at(p, (int)tile_it, total_tiles, t); ++tile_it) {
-      const TileCoord tc = decode_tile(p, t, N_TILE);
+    TileCoord tc;
+    for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, rank, tc); ++tile_it) {
       const int acc = tile_it & 1;
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
       const bool valid = gx < p.W && gy < p.H && gb < p.B;
@@ -558,7 +594,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // accumulator drained -> MMA may overwrite it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty(acc));
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(on_leader(tmem_empty(acc)));
+        else mbar_arrive(tmem_empty(acc));
+      }
 
       if (p.head_out && valid) {
         const float* hb = ss + 2 * N_TILE + 128;
@@ -580,7 +619,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) tma_store_wait_all<0>();
     if (p.stats_out) {
       bar_sync(1, kEpiThreads);
-      float* dst = p.stats_out + (size_t)blockIdx.x * (2 * N_TILE * 2);
+      // partial index i with i % num_n_tiles == this CTA's N tile (what bn_finalize assumes): a pair's two CTAs sit
+      // num_n_tiles apart
+      const int slot = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+      const int pidx = CTAS == 2 ? (slot / p.num_n_tiles) * (2 * p.num_n_tiles) + rank * p.num_n_tiles + slot % p.num_n_tiles
+                                 : slot;
+      float* dst = p.stats_out + (size_t)pidx * (2 * N_TILE * 2);
       for (int i = etid; i < 2 * N_TILE * 2; i += kEpiThreads) {
         float s = 0.f;
 #pragma unroll
@@ -592,10 +636,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's smem / TMEM are in use until the leader's last MMA has retired
+  else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem2_dealloc(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

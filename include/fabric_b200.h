@@ -58,6 +58,7 @@ typedef struct {
   int b_stages;    /* 0 = auto */
   int b_resident;  /* -1 = auto, 0 / 1 */
   int grid;        /* 0 = auto (#SMs rounded to a multiple of the N tiles) */
+  int ctas;        /* 0 = auto, 1 = one CTA per 128-pixel tile, 2 = CTA pair (tcgen05 cta_group::2, M = 256) */
 } fb_conv_tuning;
 
 typedef struct {

@@ -216,13 +216,9 @@ LAYERS = [  # name, G, H, cin, cout   (B = 64 pairs)
 def group_bench():
     B = int(os.environ.get("FB_BENCH_B", "64"))
     for name, G, H, cin, cout in LAYERS:
-        tunes = [dict(halo=0, b_resident=0)]
+        tunes = [dict(ctas=1), dict(ctas=2)]
         if cin >= 64:
-            tunes.append(dict(halo=1, b_resident=0))
-            tunes.append(dict(halo=1, b_resident=-1))
-            if cout >= 256:
-                tunes.append(dict(halo=1, n_tile=256))
-                tunes.append(dict(halo=0, n_tile=256))
+            tunes.append(dict(ctas=2, b_resident=0))
         for t in tunes:
             time_conv(name, G, B, H, H, cin, cout, t)
 
