@@ -20,7 +20,7 @@ class FabricB200Error(RuntimeError):
 
 class ConvTuning(C.Structure):
     _fields_ = [("n_tile", C.c_int), ("halo", C.c_int), ("a_stages", C.c_int), ("b_stages", C.c_int),
-                ("b_resident", C.c_int), ("grid", C.c_int), ("ctas", C.c_int)]
+                ("b_resident", C.c_int), ("grid", C.c_int), ("ctas", C.c_int), ("epi_warps", C.c_int)]
 
 
 class Conv3x3Desc(C.Structure):

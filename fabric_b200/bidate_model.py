@@ -53,8 +53,10 @@ class BiDateNet(nn.Module):
         def cat(level, cs, cl):     # decoder input [1,B,H/2^l,W/2^l,cs+cl]; skip half filled by the encoder epilogue
             return torch.empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
         cat4, cat3, cat2, cat1 = cat(0, 64, 64), cat(1, 128, 128), cat(2, 256, 256), cat(3, 512, 512)
-        e1 = self.inc.run5(x5, pool=True, prod_out=cat4)                       # models/bidate_model.py:23,29 (+ :38 skip)
-        e2 = self.down1.run5(e1["pool"], pool=True, prod_out=cat3)             # :24,30 (+ :37)
+        # the full-resolution encoder outputs are consumed only through their pooled copy and the fused product, so the
+        # 64- and 128-wide levels do not write them at all (the date-0 tile waits in shared memory for its partner)
+        e1 = self.inc.run5(x5, pool=True, prod_out=cat4, keep_main=False)      # models/bidate_model.py:23,29 (+ :38 skip)
+        e2 = self.down1.run5(e1["pool"], pool=True, prod_out=cat3, keep_main=False)   # :24,30 (+ :37)
         e3 = self.down2.run5(e2["pool"], pool=True, prod_out=cat2)             # :25,31 (+ :36)
         e4 = self.down3.run5(e3["pool"], pool=True, prod_out=cat1)             # :26,32 (+ :35)
         e5 = self.down4.run5(e4["pool"])                                       # :27,33

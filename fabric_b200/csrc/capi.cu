@@ -9,7 +9,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------ conv planning
 struct ConvPlan {
   fb::Conv3x3Params p;
-  int n_tile, ck, halo, grid, smem, ctas;
+  int n_tile, ck, halo, grid, smem, ctas, ew;
 };
 
 int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
@@ -28,9 +28,11 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (ck == 16 && n_tile != 64) return fail(FB_ERR_SHAPE, "Cin=16 path is built for n_tile 64 only");
   if (d->head_out && (d->Cout != 64 || n_tile != 64 || !d->head_w || !d->head_b))
     return fail(FB_ERR_SHAPE, "fused head needs Cout == 64 and head weights");
-  if (!d->store_main && !d->head_out) return fail(FB_ERR_ARG, "nothing to write");
-  if (d->prod_out && (d->G != 2 || !d->store_main || d->prod_channels < d->Cout || d->prod_channels % 8))
-    return fail(FB_ERR_SHAPE, "product fusion needs both date groups, the main output and prod_channels >= Cout");
+  if (!d->store_main && !d->head_out && !d->prod_out) return fail(FB_ERR_ARG, "nothing to write");
+  if (d->prod_out && (d->G != 2 || d->prod_channels < d->Cout || d->prod_channels % 8))
+    return fail(FB_ERR_SHAPE, "product fusion needs both date groups and prod_channels >= Cout");
+  if (d->prod_out && !d->store_main && n_tile > 128)
+    return fail(FB_ERR_SHAPE, "product fusion without the main output needs n_tile <= 128 (date-0 tile kept in smem)");
 
   fb::Conv3x3Params& p = pl->p;
   memset(&p, 0, sizeof(p));
@@ -51,6 +53,10 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (halo < 0) halo = halo_ok ? 1 : 0;
   if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs H > 8");
 
+  // epilogue warps: 8 (two per TMEM lane quarter) for the 64- and 128-wide tiles, whose epilogue is the bottleneck
+  int ew = d->tune.epi_warps;
+  if (ew == 0) ew = n_tile <= 128 ? 8 : 4;
+  if (!(ew == 4 || (ew == 8 && n_tile <= 128))) return fail(FB_ERR_ARG, "tune.epi_warps must be 0, 4 or (n_tile <= 128) 8");
   // CTA pairs (cta_group::2): two adjacent M tiles share one M = 256 MMA and each CTA stages half of the weight rows.
   // Needs an even number of M tiles per date-pair unit and room for at least one pair per N tile.
   const int m_units = p.num_m_tiles / (d->prod_out ? 2 : 1);   // M tiles the persistent loop enumerates
@@ -78,7 +84,11 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   // (measured: a second buffer does NOT help ordinary tiles -- the previous store has long drained -- and costs the
   //  128->64 layers their resident weights, so it is used for product pairs only)
   const int out_bufs = (d->prod_out && n_tile <= 128) ? 2 : 1;
-  const int fixed = out_bufs * 128 * n_tile * 2 + fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr) + 1024;
+  // pooled copy / product through smem staging + TMA store instead of scattered per-lane 16-byte stores
+  const int pool_tma = (d->pool_out && p.bh == 16) ? 1 : 0;
+  const int prod_tma = (d->prod_out && out_bufs == 2 && !d->store_main) ? 1 : 0;
+  const int fixed = out_bufs * 128 * n_tile * 2 + (pool_tma ? out_bufs * 4 * (n_tile / 64) * 1024 : 0) +
+                    fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr) + 1024;
   const int avail = di.smem_optin - fixed;
   const int kblocks = 9 * p.kchunks;
   int b_res = d->tune.b_resident;
@@ -117,22 +127,23 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   auto magic = [](int dv) { return (unsigned long long)(((1ULL << 40) + dv - 1) / dv); };
   p.mg_nt = magic(p.num_n_tiles), p.mg_tx = magic(p.tiles_x), p.mg_ty = magic(p.tiles_y), p.mg_tb = magic(p.tiles_b);
   if ((double)p.num_m_tiles * p.num_n_tiles * 65536.0 >= 1.0e12) return fail(FB_ERR_SHAPE, "too many tiles");
-  p.out_bufs = out_bufs;
-  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas;
+  p.out_bufs = out_bufs, p.pool_tma = pool_tma, p.prod_tma = prod_tma;
+  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas, pl->ew = ew;
   return FB_OK;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS>
-int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY, cudaStream_t st) {
-  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS>;
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW>
+int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY,
+                const CUtensorMap& tP, const CUtensorMap& tQ, cudaStream_t st) {
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS, EW>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(pl.grid), cfg.blockDim = dim3(fb::kConvThreads), cfg.dynamicSmemBytes = pl.smem, cfg.stream = st;
+  cfg.gridDim = dim3(pl.grid), cfg.blockDim = dim3(fb::conv_threads(EW)), cfg.dynamicSmemBytes = pl.smem, cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;   // a CTA pair = one cluster of 2 on one TPC
   at[0].val.clusterDim.x = CTAS, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = CTAS == 2 ? 1 : 0;
-  FB_CUDA(cudaLaunchKernelEx(&cfg, k, tA, tB, tY, pl.p));
+  FB_CUDA(cudaLaunchKernelEx(&cfg, k, tA, tB, tY, tP, tQ, pl.p));
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -162,6 +173,26 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
     for (int j = 0; j < 8; ++j) f[j] = (c0 + j < C) ? tile[(c0 + j) * P1 + x] : 0.f;
     out[i] = fb::pack8(f);
   }
+}
+
+// NCHW fp32 -> NHWC bf16 for the 13-band input (C <= 16, Cpad == 16): one thread = one pixel.  A warp reads 128
+// contiguous bytes per channel plane and writes 1 KB contiguous (one 32-byte st.global.v8 per lane): ~35 instructions
+// per pixel instead of the smem transpose's ~1000 (that kernel was issue-bound at 23 % of HBM bandwidth).
+__global__ void __launch_bounds__(256) pack_nchw16_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, int C,
+                                                          uint32_t hw, uint32_t total) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const uint32_t b = i / hw, pos = i - b * hw;
+  const float* s = src + (size_t)b * C * hw + pos;
+  float v[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(s + (size_t)c * hw) : 0.f;
+  uint32_t r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = fb::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + (size_t)i * 8), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 
 // NHWC bf16 -> NCHW fp32.  One block = 32 pixels of one row x all channels (smem transpose).
@@ -269,6 +300,53 @@ build_up_input_kernel(const uint4* __restrict__ skip, const uint4* __restrict__ 
   }
 }
 
+// Upsample-only form of the kernel above (skip half already written by the encoder's fused product): grid = (items of
+// one output row / 256, H, B), one thread = 8 channels of one output pixel, no integer division, row weights shared by
+// the block.  ~100 instructions per 16 output bytes instead of ~240 (the general kernel is issue-bound).
+template <int LG>
+__global__ void __launch_bounds__(256) upsample_into_kernel(const uint4* __restrict__ low, uint4* __restrict__ out, int H, int W,
+                                                            int Cs8, int h, int w, int Cl8, int cl8_shift, int padT, int padL,
+                                                            float sy, float sx, uint32_t low_g) {
+  const uint32_t item = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t x = cl8_shift >= 0 ? item >> cl8_shift : item / (uint32_t)Cl8;
+  if (x >= (uint32_t)W) return;
+  const uint32_t cl = item - x * Cl8;
+  const uint32_t y = blockIdx.y, b = blockIdx.z;
+  const int uy = (int)y - padT, ux = (int)x - padL;
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = 0.f;
+  if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
+    const float fy = sy * uy, fx = sx * ux;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float wgt[4] = {(1.f - ly) * (1.f - lx), (1.f - ly) * lx, ly * (1.f - lx), ly * lx};
+    const uint32_t row0 = (b * h + y0) * w, row1 = (b * h + y1) * w;
+    const uint32_t o[4] = {(row0 + x0) * Cl8 + cl, (row0 + x1) * Cl8 + cl, (row1 + x0) * Cl8 + cl, (row1 + x1) * Cl8 + cl};
+    uint4 v0[4], v1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v0[k] = __ldg(low + o[k]);
+      if (LG == 2) v1[k] = __ldg(low + o[k] + low_g);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a[8];
+      fb::unpack8(v0[k], a);
+      if (LG == 2) {
+        float c[8];
+        fb::unpack8(v1[k], c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * c[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(wgt[k], a[j], r[j]);
+    }
+  }
+  out[((b * H + y) * W + x) * (uint32_t)(Cs8 + Cl8) + Cs8 + cl] = fb::pack8(r);
+}
+
 // 1x1 head: one warp = 32 consecutive pixels, each lane one pixel; weights in smem
 __global__ void outconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ logits, int B, int H, int W, int C) {
@@ -318,6 +396,13 @@ int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, i
   if (!src || !dst) return fail(FB_ERR_ARG, "null pointer");
   if (C < 1 || Cpad < C || Cpad % 8 || B < 1 || H < 1 || W < 1 || H > 65535 || B > 65535) return fail(FB_ERR_SHAPE, "bad shape");
   if (!aligned16(dst)) return fail(FB_ERR_ALIGN, "dst must be 16-byte aligned");
+  if (C <= 16 && Cpad == 16 && ((uintptr_t)dst & 31) == 0 && (double)B * H * W < 4.0e9) {
+    const uint32_t total = (uint32_t)B * H * W;
+    pack_nchw16_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<uint32_t*>(dst), C,
+                                                                             (uint32_t)H * W, total);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+  }
   const int PX = C <= 32 ? 256 : 32;
   const size_t smem = (size_t)C * (PX + 1) * sizeof(float);
   if (smem > (size_t)di.smem_optin) return fail(FB_ERR_SHAPE, "too many channels for the pack kernel");
@@ -386,16 +471,31 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   // y may be absent (head-only): the map is still needed as a kernel argument, point it at x's storage
   // store box = one epilogue warp's 32 pixel rows
   const int bhw = p.bh < 4 ? p.bh : 4;
-  if (d->store_main) rc = make_tmap_act(&tY, d->y, p.Cout, p.W, p.H, p.B, p.G, 64, 8, bhw, 4 / bhw, CU_TENSOR_MAP_SWIZZLE_128B);
+  // store boxes: one per epilogue warp -- 64 channels (128B swizzle) with 4 warps, 32 channels (64B swizzle) with 8
+  const int sbc = pl.ew == 8 ? 32 : 64;
+  const CUtensorMapSwizzle ssw = pl.ew == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (d->store_main) rc = make_tmap_act(&tY, d->y, p.Cout, p.W, p.H, p.B, p.G, sbc, 8, bhw, 4 / bhw, ssw);
   else tY = tA;
+  if (rc) return rc;
+  CUtensorMap tP = tA, tQ = tA;   // unused maps still have to be valid kernel arguments
+  if (p.prod_tma) rc = make_tmap_act(&tP, d->prod_out, p.prod_ct, p.W, p.H, p.B, 1, sbc, 8, bhw, 4 / bhw, ssw);
+  if (rc) return rc;
+  if (p.pool_tma) rc = make_tmap_act(&tQ, d->pool_out, p.Cout, p.W / 2, p.H / 2, p.B, p.G, sbc, 4, 2, 1, ssw);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const bool res = p.b_resident != 0;
+#define FB_LAUNCH(NT, CK, HL, RS, EW)                                                                   \
+  {                                                                                                     \
+    if (pl.ctas == 2) return launch_conv<NT, CK, HL, RS, 2, EW>(pl, tA, tB, tY, tP, tQ, st);            \
+    return launch_conv<NT, CK, HL, RS, 1, EW>(pl, tA, tB, tY, tP, tQ, st);                              \
+  }
 #define FB_DISPATCH(NT, CK, HL, RS)                                                                     \
   if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) {                            \
-    if (pl.ctas == 2) return launch_conv<NT, CK, HL, RS, 2>(pl, tA, tB, tY, st);                        \
-    return launch_conv<NT, CK, HL, RS, 1>(pl, tA, tB, tY, st);                                          \
+    if (pl.ew == 8) FB_LAUNCH(NT, CK, HL, RS, 8)                                                        \
+    FB_LAUNCH(NT, CK, HL, RS, 4)                                                                        \
   }
+#define FB_DISPATCH4(NT, CK, HL, RS) \
+  if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) FB_LAUNCH(NT, CK, HL, RS, 4)
   FB_DISPATCH(64, 16, false, true)
   FB_DISPATCH(64, 16, true, true)
   FB_DISPATCH(64, 64, false, false)
@@ -406,8 +506,10 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   FB_DISPATCH(128, 64, false, true)
   FB_DISPATCH(128, 64, true, false)
   FB_DISPATCH(128, 64, true, true)
-  FB_DISPATCH(256, 64, false, false)
-  FB_DISPATCH(256, 64, true, false)
+  FB_DISPATCH4(256, 64, false, false)
+  FB_DISPATCH4(256, 64, true, false)
+#undef FB_DISPATCH4
+#undef FB_LAUNCH
 #undef FB_DISPATCH
   return fail(FB_ERR_SHAPE, "no kernel for n_tile %d ck %d halo %d resident %d", pl.n_tile, pl.ck, pl.halo, (int)res);
 }
@@ -433,6 +535,24 @@ int fabric_b200_build_up_input(const void* skip, const void* low, void* out, int
   if (Cs % 8 || Cl % 8 || 2 * h > H || 2 * w > W || (low_groups != 1 && low_groups != 2)) return fail(FB_ERR_SHAPE, "bad shape");
   if ((double)B * H * W * (Cs + Cl) / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   if (!aligned16(skip) || !aligned16(low) || !aligned16(out)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
+  if (!skip && H <= 65535 && B <= 65535) {
+    const int Cl8 = Cl / 8;
+    int shift = -1;
+    for (int sft = 0; sft < 12; ++sft)
+      if ((1 << sft) == Cl8) shift = sft;
+    const float sy = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+    const float sx = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+    dim3 grid(((size_t)W * Cl8 + 255) / 256, H, B);
+    const uint32_t low_g = (uint32_t)B * h * w * Cl8;
+    if (low_groups == 2)
+      upsample_into_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(low), reinterpret_cast<uint4*>(out),
+                                                                      H, W, Cs / 8, h, w, Cl8, shift, (H - 2 * h) / 2, (W - 2 * w) / 2, sy, sx, low_g);
+    else
+      upsample_into_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(low), reinterpret_cast<uint4*>(out),
+                                                                      H, W, Cs / 8, h, w, Cl8, shift, (H - 2 * h) / 2, (W - 2 * w) / 2, sy, sx, low_g);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+  }
   const size_t n = (size_t)B * H * W * (skip ? Cs + Cl : Cl) / 8;
   build_up_input_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(skip), reinterpret_cast<const uint4*>(low), reinterpret_cast<uint4*>(out), B, H, W, Cs,

@@ -48,15 +48,17 @@ struct Conv3x3Params {
   int prod_ct;
   int pair_dates;  // 1: iterate tiles as date pairs (needs G == 2)
   int out_bufs;    // 1 or 2 output staging buffers; 2 keeps the date-0 tile in smem for the date-1 product
+  int pool_tma;    // pooled copy leaves through per-warp smem staging + TMA store (16-row tiles) instead of per-lane stores
+  int prod_tma;    // product leaves through the date-1 staging buffer + TMA store (two buffers, no main output)
   unsigned long long mg_nt, mg_tx, mg_ty, mg_tb;  // fast_div magics for num_n_tiles, tiles_x, tiles_y, tiles_b
 };
 
-// warps [0, kEpiThreads/32): epilogue; then the TMA producer warp; then the MMA issuer warp LAST: the warp scheduler
-// arbitrates in favour of the higher warp id, and the MMA warp's instruction stream is the kernel's critical path.
-// (Eight epilogue warps were measured: no gain on the 64-wide layers, -15 % on the 256-wide ones.)
-constexpr int kEpiThreads = 128;
-constexpr int kEpiGroups = kEpiThreads / 128;
-constexpr int kConvThreads = kEpiThreads + 64;
+// warps [0, EW): epilogue; then the TMA producer warp; then the MMA issuer warp LAST: the warp scheduler arbitrates in
+// favour of the higher warp id, and the MMA warp's instruction stream is the kernel's critical path.
+// EW = 4: one warp per TMEM lane quarter.  EW = 8: two warps per quarter, warp group eg = warp / 4 takes every other
+// 32-column chunk -- the epilogue of a 64- or 128-wide tile (~420 instructions per chunk with pool / product / moments,
+// one warp per scheduler, nothing to hide latency with) was measured to be the bottleneck of those layers.
+__host__ __device__ constexpr int conv_threads(int EW) { return EW * 32 + 64; }
 constexpr int kHaloW = 10, kHaloH = 18;
 constexpr int kHaloBytes = kHaloW * kHaloH * 128;  // 23040
 constexpr int kHaloStage = 23552;                  // rounded up to 1024
@@ -71,7 +73,7 @@ __host__ __device__ constexpr int conv_stats_bytes(int N_TILE) { return 4 * 2 * 
 __host__ __device__ constexpr int conv_misc_bytes(int N_TILE, bool stats) {
   // scale/shift + head weights (+ head exchange with two epilogue groups), stats slabs (only when BN moments are
   // requested), barriers + tmem pointer
-  return (2 * N_TILE + 136 + (kEpiGroups == 2 ? 256 : 0)) * 4 + (stats ? conv_stats_bytes(N_TILE) : 0) + 1024;
+  return (2 * N_TILE + 136 + 256) * 4 + (stats ? conv_stats_bytes(N_TILE) : 0) + 1024;
 }
 
 // column sums over the 32 lanes of a warp: returns sum_lanes v[lane_id]  (31 shuffles instead of 160)
@@ -145,15 +147,19 @@ __device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int N_TI
   return true;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW>
+__global__ void __launch_bounds__(conv_threads(EW), 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmY, const Conv3x3Params p) {
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP,
+                    const __grid_constant__ CUtensorMap tmQ, const Conv3x3Params p) {
+  // tmP: decoder input [1,B,H,W,Ct] (fused product, same per-warp box as tmY); tmQ: pooled output, box 64 ch x 4 x 2
   // tmY: output map with the PER-WARP store box (64 ch x 8 x min(bh,4) x 4/min(bh,4)): each epilogue warp stores its
   // own 32 pixel rows, so the four warps never synchronise with each other in steady state
   static_assert(CK == 64 || CK == 16, "channel chunk is 64 (128B swizzle) or 16 (32B swizzle)");
   static_assert(N_TILE == 64 || N_TILE == 128 || N_TILE == 256, "N tile");
   static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair (cta_group::2) per tile row");
+  static_assert(EW == 4 || EW == 8, "four or eight epilogue warps");
+  constexpr int kEpiThreads = EW * 32, kEpiGroups = EW / 4;
   constexpr int A_BYTES = conv_a_stage_bytes(CK, HALO);
   constexpr int A_TX = HALO ? kHaloW * kHaloH * CK * 2 : 128 * CK * 2;
   constexpr int B_BYTES = conv_b_stage_bytes(N_TILE, CK) / CTAS;   // a CTA of a pair stages half of the weight rows
@@ -174,8 +180,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t a_off = 0;
   const uint32_t b_off = a_off + p.a_stages * A_BYTES;
   const uint32_t out_off = b_off + p.b_stages * B_BYTES;
-  const uint32_t ss_off = out_off + p.out_bufs * OUT_BYTES;
-  const uint32_t st_off = ss_off + (2 * N_TILE + 136 + (kEpiGroups == 2 ? 256 : 0)) * 4;
+  constexpr int POOL_BYTES = 4 * (N_TILE / 64) * 1024;   // per buffer: 4 warps x 8 pooled pixels x N_TILE channels
+  const uint32_t pool_off = out_off + p.out_bufs * OUT_BYTES;
+  const uint32_t ss_off = pool_off + (p.pool_tma ? p.out_bufs * POOL_BYTES : 0);
+  const uint32_t st_off = ss_off + (2 * N_TILE + 136 + 256) * 4;
   const uint32_t bar_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
 
   float* ss = reinterpret_cast<float*>(sm + ss_off);       // [0,N) scale, [N,2N) shift, [2N,2N+128) head w, +128.. head b
@@ -202,6 +210,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
+    if (p.prod_tma) prefetch_tmap(&tmP);
+    if (p.pool_tma) prefetch_tmap(&tmQ);
   }
   if (warp == kMmaWarp) {
     if (CTAS == 2) {
@@ -457,14 +467,30 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool affine = p.scale != nullptr || p.shift != nullptr;
     const bool relu = p.relu != 0;
     const bool extras = p.stats_out || p.pool_out || p.prod_out || p.head_out;   // one branch for the common plain tile
+    // epilogue options as ONE opaque register: the chunk loop tests bits instead of re-reading kernel parameters through
+    // the constant bank (LDCU + ISETP + BRA per test, each a latency bubble with one or two warps per scheduler)
+    enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128 };
+    uint32_t flags = (p.store_main ? F_MAIN : 0u) | (p.prod_out ? F_PROD : 0u) | (p.stats_out ? F_STATS : 0u) |
+                     (p.pool_out ? F_POOL : 0u) | (p.pool_tma ? F_POOL_TMA : 0u) | (p.prod_tma ? F_PROD_TMA : 0u) |
+                     (p.head_out ? F_HEAD : 0u) | (p.out_bufs == 2 ? F_TWO : 0u);
+    asm volatile("mov.b32 %0, %0;" : "+r"(flags));
+    const int pH = p.H, pW = p.W, pB = p.B, pCout = p.Cout, pCt = p.prod_ct;
     int cur_n0 = -1;
     uint32_t tile_it = 0;
+    // Output staging (what the TMA stores read).  EW = 4: per 64-channel group a [128 px][128 B] slab, 128B swizzle, one
+    // store box of 64 ch x 32 px per warp.  EW = 8: per 32-channel chunk a [128 px][64 B] slab, 64B swizzle, one store
+    // box of 32 ch x 32 px per warp -- the two warps of a lane quarter never have to meet.
+    auto stage_ptr = [&](uint8_t* buf, int cc, int i) -> uint4* {   // 16-byte piece i (0..3) of chunk cc, this thread's row
+      if (kEpiGroups == 1) return reinterpret_cast<uint4*>(buf + (cc >> 1) * 16384 + m * 128 + ((((cc & 1) * 4 + i) ^ (m & 7)) * 16));
+      return reinterpret_cast<uint4*>(buf + cc * 8192 + m * 64 + ((i ^ ((m >> 1) & 3)) * 16));
+    };
+    float* hx = ss + 2 * N_TILE + 136;   // [128][2] head partial sums handed from warp group 1 to group 0 (EW = 8)
     bar_sync(1, kEpiThreads);   // stats / head constants visible; the ONLY CTA-wide epilogue barrier in steady state
     TileCoord tc;
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, rank, tc); ++tile_it) {
       const int acc = tile_it & 1;
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
-      const bool valid = gx < p.W && gy < p.H && gb < p.B;
+      const bool valid = gx < pW && gy < pH && gb < pB;
       if (tc.n0 != cur_n0) {
         // (once per CTA when the grid is a multiple of the N tiles) the warps are not in lockstep: fence both sides
         bar_sync(1, kEpiThreads);
@@ -476,12 +502,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bar_sync(1, kEpiThreads);
       }
       // output staging: with two buffers the previous tile stays readable in smem (date-0 tile of a product pair)
-      const int ob = p.out_bufs == 2 ? (int)(tile_it & 1) : 0;
+      const int ob = (flags & F_TWO) ? (int)(tile_it & 1) : 0;
       uint8_t* out_sm = sm + out_off + ob * OUT_BYTES;
       const uint8_t* prev_sm = sm + out_off + (ob ^ 1) * OUT_BYTES;
-      const bool prod_tile = p.prod_out && tc.g == 1;
+      const bool prod_tile = (flags & F_PROD) && tc.g == 1;
       if (lane == 0) {   // this warp's own earlier stores
-        if (p.out_bufs == 2) tma_store_wait_read<1>();           // the store issued two tiles ago has drained this buffer
+        if ((flags & F_TWO)) tma_store_wait_read<1>();           // the store issued two tiles ago has drained this buffer
         else if (prod_tile) tma_store_wait_all<0>();             // single buffer: date-0 rows are re-read from L2
         else tma_store_wait_read<0>();
       }
@@ -514,17 +540,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 
         // staging for the TMA store: sub-tile (cc/2) of 64 channels, row m, 16-byte chunk index XOR (m & 7)
-        {
-          uint8_t* row = out_sm + (cc >> 1) * 16384 + m * 128;
-          const int cbase = (cc & 1) * 4;
+        // (without a main output only the date-0 tile of a product pair is staged: its date-1 partner reads it back)
+        if ((flags & F_MAIN) || ((flags & F_PROD) && tc.g == 0)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int chunk = (cbase + i) ^ (m & 7);
-            *reinterpret_cast<uint4*>(row + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
+          for (int i = 0; i < 4; ++i) *stage_ptr(out_sm, cc, i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
         if (extras) {
-        if (p.stats_out) {
+        if ((flags & F_STATS)) {
           // moments of the values as stored (bf16-rounded), invalid (out-of-image) pixels contribute 0
           float s1[32], s2[32];
 #pragma unroll
@@ -541,7 +563,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           dst[0] += cs1;
           dst[1] += cs2;
         }
-        if (p.pool_out) {
+        if ((flags & F_POOL)) {
           // 2x2 max over (x^1, y^1) neighbours = lanes ^1 and ^8 of the same warp
           uint32_t pm[16];
 #pragma unroll
@@ -549,36 +571,47 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t a = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
             pm[j] = bf16x2_max(a, __shfl_xor_sync(0xffffffffu, a, 8));
           }
-          const int Hp = p.H >> 1, Wp = p.W >> 1;
-          if (!(px & 1) && !(py & 1) && (gx >> 1) < Wp && (gy >> 1) < Hp && gb < p.B) {
-            size_t off = ((((size_t)tc.g * p.B + gb) * Hp + (gy >> 1)) * Wp + (gx >> 1)) * p.Cout + tc.n0 + cc * 32;
+          const int Hp = pH >> 1, Wp = pW >> 1;
+          if ((flags & F_POOL_TMA)) {
+            // this warp's 4 tile rows x 8 columns pool to 2 x 4 pixels: row r of a 128B-swizzled [8][64 ch] slab per
+            // 64-channel group; the TMA store clips whatever lies outside the pooled image
+            if (!(lane & 9)) {   // even column, even row
+              const int r = ((lane >> 4) << 2) | ((lane & 7) >> 1);
+              uint8_t* pbuf = sm + pool_off + ob * POOL_BYTES + q * ((N_TILE / 64) * 1024);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint8_t* dstp = kEpiGroups == 1 ? pbuf + (cc >> 1) * 1024 + r * 128 + ((((cc & 1) * 4 + i) ^ r) * 16)
+                                                : pbuf + cc * 512 + r * 64 + ((i ^ ((r >> 1) & 3)) * 16);
+                *reinterpret_cast<uint4*>(dstp) = make_uint4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2], pm[4 * i + 3]);
+              }
+            }
+          } else if (!(px & 1) && !(py & 1) && (gx >> 1) < Wp && (gy >> 1) < Hp && gb < pB) {
+            size_t off = ((((size_t)tc.g * pB + gb) * Hp + (gy >> 1)) * Wp + (gx >> 1)) * pCout + tc.n0 + cc * 32;
             uint4* dst = reinterpret_cast<uint4*>(p.pool_out + off);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2], pm[4 * i + 3]);
           }
         }
-        if (prod_tile && valid) {
+        if (prod_tile && (valid || (flags & F_PROD_TMA))) {
           // relu(d2 * d1): this tile is date 1; the same CTA produced the date-0 tile one iteration ago.  With two
           // staging buffers this thread re-reads ITS OWN row of that tile from smem, otherwise from L2.
-          const size_t pix = ((size_t)gb * p.H + gy) * p.W + gx;
+          const size_t pix = ((size_t)gb * pH + gy) * pW + gx;
           const uint4* a0 = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(p.y0_ptr) + pix * p.Cout + tc.n0 + cc * 32);
-          const uint8_t* prow = prev_sm + (cc >> 1) * 16384 + m * 128;
-          uint4* dst = reinterpret_cast<uint4*>(p.prod_out + pix * p.prod_ct + tc.n0 + cc * 32);
+              reinterpret_cast<const __nv_bfloat16*>(p.y0_ptr) + pix * pCout + tc.n0 + cc * 32);
+          uint4* dst = reinterpret_cast<uint4*>(p.prod_out + pix * pCt + tc.n0 + cc * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 o = p.out_bufs == 2 ? *reinterpret_cast<const uint4*>(prow + ((((cc & 1) * 4 + i) ^ (m & 7)) * 16))
-                                            : __ldcg(a0 + i);
+            const uint4 o = (flags & F_TWO) ? *stage_ptr(const_cast<uint8_t*>(prev_sm), cc, i) : __ldcg(a0 + i);
+            // packed bf16 multiply: the fp32 product of two bf16 values is exact, so one rounding either way
             const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
             uint32_t rv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              rv[k] = pack_bf16x2(fmaxf(bf16_lo(pk[4 * i + k]) * bf16_lo(ov[k]), 0.f),
-                                  fmaxf(bf16_hi(pk[4 * i + k]) * bf16_hi(ov[k]), 0.f));
-            dst[i] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+            for (int k = 0; k < 4; ++k) rv[k] = bf16x2_max(bf16x2_mul(pk[4 * i + k], ov[k]), 0u);
+            if ((flags & F_PROD_TMA)) *stage_ptr(out_sm, cc, i) = make_uint4(rv[0], rv[1], rv[2], rv[3]);   // date-1 tile's own buffer
+            else dst[i] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
           }
         }
-        if (p.head_out) {
+        if ((flags & F_HEAD)) {
           const float* hw = ss + 2 * N_TILE;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -599,20 +632,42 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else mbar_arrive(tmem_empty(acc));
       }
 
-      if (p.head_out && valid) {
+      if (kEpiGroups == 2 && (flags & F_HEAD)) {   // each group summed its own 32 channels: group 1 hands its part to group 0
+        if (eg == 1) {
+          hx[2 * m] = head0;
+          hx[2 * m + 1] = head1;
+        }
+        bar_sync(2 + q, 64);
+        if (eg == 0) {
+          head0 += hx[2 * m];
+          head1 += hx[2 * m + 1];
+        }
+        bar_sync(2 + q, 64);   // hx is free again before group 1 reaches the next tile
+      }
+      if ((flags & F_HEAD) && valid && eg == 0) {
         const float* hb = ss + 2 * N_TILE + 128;
-        const size_t img = (size_t)tc.g * p.B + gb;
-        const size_t plane = (size_t)p.H * p.W;
-        p.head_out[(img * 2 + 0) * plane + (size_t)gy * p.W + gx] = head0 + hb[0];
-        p.head_out[(img * 2 + 1) * plane + (size_t)gy * p.W + gx] = head1 + hb[1];
+        const size_t img = (size_t)tc.g * pB + gb;
+        const size_t plane = (size_t)pH * pW;
+        p.head_out[(img * 2 + 0) * plane + (size_t)gy * pW + gx] = head0 + hb[0];
+        p.head_out[(img * 2 + 1) * plane + (size_t)gy * pW + gx] = head1 + hb[1];
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && p.store_main) {
+      if (lane == 0) {
+        // this warp's boxes: EW = 4 -> 64 channels x 32 px per 64-channel group; EW = 8 -> 32 channels x 32 px per chunk
+        constexpr int NBOX = kEpiGroups == 1 ? N_TILE / 64 : NCHUNK / 2;
+        const uint32_t obuf = base + out_off + ob * OUT_BYTES, pbuf = base + pool_off + ob * POOL_BYTES + q * ((N_TILE / 64) * 1024);
 #pragma unroll
-        for (int j = 0; j < N_TILE / 64; ++j)
-          tma_store_5d(&tmY, base + out_off + ob * OUT_BYTES + j * 16384 + q * 4096, tc.n0 + j * 64, tc.x0, tc.y0 + wy,
-                       tc.b0 + wn, tc.g);
+        for (int j = 0; j < NBOX; ++j) {
+          const int cc = 2 * j + eg;   // (EW = 8) chunk of box j
+          const uint32_t src = kEpiGroups == 1 ? obuf + j * 16384 + q * 4096 : obuf + cc * 8192 + q * 2048;
+          const int ch = tc.n0 + (kEpiGroups == 1 ? j * 64 : cc * 32);
+          if ((flags & F_MAIN)) tma_store_5d(&tmY, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, tc.g);
+          if ((flags & F_PROD_TMA) && tc.g == 1) tma_store_5d(&tmP, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, 0);
+          if ((flags & F_POOL_TMA))
+            tma_store_5d(&tmQ, kEpiGroups == 1 ? pbuf + j * 1024 : pbuf + cc * 512, ch, tc.x0 >> 1, (tc.y0 >> 1) + 2 * q, tc.b0,
+                         tc.g);
+        }
         tma_store_commit();
       }
     }

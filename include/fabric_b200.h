@@ -59,6 +59,7 @@ typedef struct {
   int b_resident;  /* -1 = auto, 0 / 1 */
   int grid;        /* 0 = auto (#SMs rounded to a multiple of the N tiles) */
   int ctas;        /* 0 = auto, 1 = one CTA per 128-pixel tile, 2 = CTA pair (tcgen05 cta_group::2, M = 256) */
+  int epi_warps;   /* 0 = auto, 4 or 8 epilogue warps (8 only for n_tile <= 128) */
 } fb_conv_tuning;
 
 typedef struct {

@@ -144,6 +144,13 @@ def test_conv3x3_fused_date_product(cuda, H, W, cin, cout, tune):
     assert torch.equal(fused["y"], plain)
     assert torch.equal(cat[0, ..., :cout], torch.relu(plain[0].float() * plain[1].float()).bfloat16())
     assert bool((cat[0, ..., cout:] == 7.0).all())                 # the upsample half is left untouched
+    if cout <= 128:
+        # eval-mode variant: the full-resolution output is not written at all, only the pooled copy and the product
+        cat2 = torch.full_like(cat, 7.0)
+        lean = ops.conv3x3(x5, wp, cout, relu=True, tune=tune, prod_out=cat2, pool=True, store_main=False)
+        assert lean["y"] is None
+        assert torch.equal(cat2, cat)
+        assert torch.equal(lean["pool"], fused["pool"])
 
 
 def test_fused_and_unfused_decoder_inputs_agree(cuda):

@@ -23,7 +23,30 @@ wp = ops.pack_conv_weight(w, 0)
 scale = torch.ones(cout, device="cuda")
 shift = torch.zeros(cout, device="cuda")
 out = torch.empty(G, B, H, H, cout, device="cuda", dtype=torch.bfloat16)
-for _ in range(iters):
-    ops.conv3x3(x5, wp, cout, scale, shift, relu=True, tune=tune, out=out)
+mode = os.environ.get("FB_MODE", "plain")   # plain | pool | prod | lean (= pool + prod, no main output) | stats
+kw = {}
+if mode in ("pool", "lean"):
+    kw["pool"] = True
+if mode in ("prod", "lean"):
+    kw["prod_out"] = torch.empty(1, B, H, H, 2 * cout, device="cuda", dtype=torch.bfloat16)
+if mode == "lean":
+    kw["store_main"] = False
+    out = None
+if mode == "stats":
+    kw["stats"] = True
+
+
+def run(n):
+    for _ in range(n):
+        ops.conv3x3(x5, wp, cout, scale, shift, relu=True, tune=tune, out=out, **kw)
+
+
+run(3)
 torch.cuda.synchronize()
-print("done", name, tune)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+run(iters)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+print("done", name, mode, tune, "ms=%.4f tflops=%.1f" % (ms, 2.0 * G * B * H * H * 9 * cin * cout / ms / 1e9))
