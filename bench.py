@@ -374,17 +374,22 @@ def main():
     hp2 = torch.randn(PAIRS, 13, SIZE, SIZE).pin_memory()
     if train:
         # reference train.py:83-95 per batch: host batch -> device, step, loss back to the host (.item(), helpers.py:83)
+        # the copy of batch i+1 overlaps step i (fabric_b200.inference.BatchFeeder); the loss of step i comes back every step
+        from fabric_b200.inference import BatchFeeder
         hlab = (torch.rand(PAIRS, SIZE, SIZE) < 0.1).long().pin_memory()
-        dx1, dx2, dlab = torch.empty_like(x1), torch.empty_like(x2), torch.empty_like(labels)
+        feeder = BatchFeeder(dev)
+        feeder.prefetch((hp1, hp2, hlab))
 
         def e2e_step():
-            dx1.copy_(hp1, non_blocking=True)
-            dx2.copy_(hp2, non_blocking=True)
-            dlab.copy_(hlab, non_blocking=True)
-            return step(dx1, dx2, dlab).item()
+            a, b, lab = feeder.next()
+            feeder.prefetch((hp1, hp2, hlab))          # next step's inputs: H2D on the side stream while this step runs
+            loss = step(a, b, lab)
+            feeder.release()
+            return loss.item()
         h2d = 2 * hp1.numel() * 4 + hlab.numel() * 8
         d2h = 4
-        api = "model(x1,x2); TverskyLoss(logits, labels); loss.backward(); DataParallelStep.sync(); SGD.step(); loss.item()"
+        api = ("BatchFeeder.next(); model(x1,x2); TverskyLoss(logits, labels); loss.backward(); DataParallelStep.sync(); "
+               "SGD.step(); loss.item()")
     else:
         hout = torch.empty(PAIRS, 2, SIZE, SIZE).pin_memory()
         pipe = HostPipeline(model, chunk=16, n_channels=13, size=SIZE, return_logits=True)

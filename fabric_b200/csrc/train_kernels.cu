@@ -534,6 +534,147 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwd p, const flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------- both dates at once
+// The encoder's second convs carry the product fusion (bidate_model.py:35-38): date g's gradient needs the OTHER date's
+// activation and both dates share one upstream gradient,
+//     dy_g = 1[a_g > 0] * ( ga * a_{1-g} + unpool(gp_g) ).
+// Walking the two date groups one after the other (kernels above) reads a0, a1 and ga twice per pass (8.5 tensor units of
+// HBM traffic); here one thread handles 8 channels of one pixel for BOTH dates, so z0, z1, a0, a1, ga, gp cross HBM once
+// per pass (5.25 units).  a_g > 0 is the ReLU mask (a = relu(bn(z)) as stored), so scale / shift are not needed.
+template <bool GP>
+__device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_t c8, uint32_t npix, float (&dy)[2][8],
+                                           float (&zf)[2][8]) {
+  const uint32_t C8 = p.C >> 3;
+  uint4 zr[2], ar[2], gpr[2], wv[2][4];
+  const uint4 gar = __ldg(p.ga + (size_t)pix * p.ga_c8 + c8);
+  bool pool_ok = false;
+  uint32_t me = 0;
+  if (GP) {
+    const uint32_t W = p.W, H = p.H, Hp = H >> 1, Wp = W >> 1;
+    const uint32_t x = pix % W, t = pix / W, y = t % H, b = t / H;
+    pool_ok = (y >> 1) < Hp && (x >> 1) < Wp;
+    me = (y & 1) * 2 + (x & 1);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (pool_ok) {
+        const size_t w00 = (size_t)(g * npix + pix - (y & 1) * W - (x & 1)) * C8 + c8;
+        wv[g][0] = __ldg(p.a + w00), wv[g][1] = __ldg(p.a + w00 + C8), wv[g][2] = __ldg(p.a + w00 + (size_t)W * C8),
+        wv[g][3] = __ldg(p.a + w00 + (size_t)(W + 1) * C8);
+        gpr[g] = __ldg(p.gp + (size_t)(((g * p.B + b) * Hp + (y >> 1)) * Wp + (x >> 1)) * C8 + c8);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    zr[g] = __ldg(p.z + (size_t)(g * npix + pix) * C8 + c8);
+    ar[g] = __ldg(p.a + (size_t)(g * npix + pix) * C8 + c8);
+  }
+  float gaf[8], af[2][8];
+  unpack8(gar, gaf);
+  unpack8(ar[0], af[0]);
+  unpack8(ar[1], af[1]);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    unpack8(zr[g], zf[g]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dy[g][j] = gaf[j] * af[1 - g][j];
+    if (GP && pool_ok) {
+      // nn.MaxPool2d backward: the pooled gradient goes to the FIRST maximum of the 2x2 window in scan order
+      float m[8], gpv[8];
+      int best[8];
+      unpack8(wv[g][0], m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = 0;
+#pragma unroll
+      for (int d = 1; d < 4; ++d) {
+        float v[8];
+        unpack8(wv[g][d], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > m[j]) m[j] = v[j], best[j] = d;
+      }
+      unpack8(gpr[g], gpv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (best[j] == (int)me) dy[g][j] += gpv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(af[g][j] > 0.f)) dy[g][j] = 0.f;
+  }
+}
+
+template <bool GP>
+__global__ void __launch_bounds__(256, 2) bn_bwd2_reduce_kernel(BnBwd p, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [blockDim][16]
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
+  const uint32_t npix = (uint32_t)p.B * p.H * p.W;
+  const uint32_t stride = gridDim.x * ppb;
+  float s1[2][8], s2[2][8], mu[2][8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    ld8f(p.mean + g * p.C + c8 * 8, mu[g]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[g][j] = s2[g][j] = 0.f;
+  }
+  for (uint32_t q = blockIdx.x * ppb + lane_p; q < npix; q += stride) {
+    float dy[2][8], zf[2][8];
+    bn_bwd2_dy<GP>(p, q, c8, npix, dy, zf);
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[g][j] += dy[g][j];
+        s2[g][j] = fmaf(dy[g][j], zf[g][j] - mu[g][j], s2[g][j]);   // x invstd once, below
+      }
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float is[8];
+    ld8f(p.invstd + g * p.C + c8 * 8, is);
+    __syncthreads();
+    float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[j] = s1[g][j], mine[8 + j] = s2[g][j] * is[j];
+    __syncthreads();
+    float* dst = partial + ((size_t)blockIdx.x * p.G + g) * p.C * 2;
+    for (int i = threadIdx.x; i < p.C * 2; i += blockDim.x) {
+      const int c = i >> 1, k = i & 1;
+      float s = 0.f;
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
+      dst[i] = s;
+    }
+  }
+}
+
+template <bool GP>
+__global__ void __launch_bounds__(256, 2) bn_bwd2_apply_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
+  const uint32_t C8 = p.C >> 3;
+  const uint32_t npix = (uint32_t)p.B * p.H * p.W;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = gtid % C8;
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;   // host guarantees divisibility
+  float k0[2][8], kz[2][8], kc[2][8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, k0[g]);
+    ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kz[g]);
+    ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc[g]);
+  }
+  for (uint32_t q = gtid / C8; q < npix; q += pstride) {
+    float dy[2][8], zf[2][8];
+    bn_bwd2_dy<GP>(p, q, c8, npix, dy, zf);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(k0[g][j], dy[g][j], fmaf(kz[g][j], zf[g][j], kc[g][j]));
+      dz[(size_t)(g * npix + q) * C8 + c8] = pack8(r);
+    }
+  }
+}
+
 // ================================================================================================ decoder-input adjoint
 // dlow[b][i][j][c] = sum_{u,v} wy(u,i) wx(v,j) dcat[b][u+padT][v+padL][Cs+c]   (adjoint of bilinear x2 + pad)
 __global__ void __launch_bounds__(256, 4)
@@ -789,12 +930,18 @@ int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga
   const int nblk = di.sms * 2;   // = resident blocks (256 threads, 2 per SM): one balanced wave
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
-  bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+  // product-fused encoder levels: both date groups per thread (see bn_bwd2_dy)
+  const bool dual = mul_other && G == 2 && ga && ga_groups == 1;
+  if (dual && gp) bn_bwd2_reduce_kernel<true><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+  else if (dual) bn_bwd2_reduce_kernel<false><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+  else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
   FB_CUDA(cudaGetLastError());
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, G, C, (double)B * H * W, gamma, invstd, mean, dgamma, dbeta, coef);
   FB_CUDA(cudaGetLastError());
   const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
-  bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+  if (dual && gp) bn_bwd2_apply_kernel<true><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+  else if (dual) bn_bwd2_apply_kernel<false><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+  else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

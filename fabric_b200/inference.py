@@ -58,6 +58,47 @@ class HostPipeline:
         return h2d, d2h
 
 
+class BatchFeeder:
+    """Host -> device hand-off for the training loop (reference train.py:80-84: the DataLoader yields host batches and the
+    loop calls ``.to(device)`` synchronously before every step).  Here the copy of batch i+1 runs on a side stream into
+    the other half of a double buffer while step i computes; ``next()`` returns device tensors that are safe to use on
+    the current stream.  Feed it pinned host tensors (``DataLoader(pin_memory=True)``)."""
+
+    def __init__(self, device):
+        self.dev = torch.device(device)
+        self.stream = torch.cuda.Stream(self.dev)
+        self.slots = [dict(t=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        self.i = 0
+        self.pending = None
+
+    def _stage(self, host_batch):
+        slot = self.slots[self.i & 1]
+        self.i += 1
+        if slot["t"] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot["t"], host_batch)):
+            slot["t"] = [torch.empty(h.shape, dtype=h.dtype, device=self.dev) for h in host_batch]
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(slot["free"])       # the step that last read this slot has finished
+            for d, h in zip(slot["t"], host_batch):
+                d.copy_(h, non_blocking=True)
+            slot["ready"].record(self.stream)
+        return slot
+
+    def prefetch(self, host_batch):
+        """Start copying ``host_batch`` (a tuple of host tensors); returns the number of bytes queued."""
+        self.pending = self._stage(host_batch)
+        return sum(h.numel() * h.element_size() for h in host_batch)
+
+    def next(self):
+        """Device tensors of the batch given to the last ``prefetch``; call ``release()`` after the step is enqueued."""
+        slot, self.pending = self.pending, None
+        torch.cuda.current_stream(self.dev).wait_event(slot["ready"])
+        self.current = slot
+        return slot["t"]
+
+    def release(self):
+        self.current["free"].record(torch.cuda.current_stream(self.dev))
+
+
 def predict_patches(model, p1, p2, batch_size: int = 16, return_logits: bool = False,
                     pipeline: Optional[HostPipeline] = None):
     """Drop-in for the loop at reference train.py:187-201: ``p1``/``p2`` are host arrays [N,13,S,S] fp32 (as

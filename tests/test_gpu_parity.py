@@ -362,3 +362,24 @@ def test_predict_scene_matches_reference_pipeline(cuda):
     ref = O.get_bands(torch.max(logits, 1)[1].numpy().astype(np.float64), hs, ws, lc, lr, h, w, p)
     agree = (canvas.cpu().numpy().astype(np.float64) == ref).mean()
     assert agree >= 0.999, agree
+
+
+def test_batch_feeder_double_buffer(cuda):
+    """Host batches staged on the side stream arrive intact and in order, also when the consumer is slow."""
+    from fabric_b200.inference import BatchFeeder
+    feeder = BatchFeeder(cuda)
+    batches = [(torch.full((4, 13, 16, 16), float(i)).pin_memory(), torch.full((4, 16, 16), i, dtype=torch.int64).pin_memory())
+               for i in range(5)]
+    feeder.prefetch(batches[0])
+    seen = []
+    for i in range(5):
+        x, lab = feeder.next()
+        if i + 1 < 5:
+            feeder.prefetch(batches[i + 1])
+        y = (x * 2).sum() + lab.sum()          # "the step"
+        torch.cuda._sleep(2_000_000)           # keep the stream busy while the next copy lands in the other slot
+        seen.append(y)
+        feeder.release()
+    torch.cuda.synchronize()
+    for i, y in enumerate(seen):
+        assert float(y) == 2.0 * i * 4 * 13 * 256 + i * 4 * 256

@@ -142,7 +142,7 @@ def test_up_input_bwd_is_adjoint_of_bilinear_pad(cuda, H, W, h, w):
     assert rel(dlow[0].float(), low.grad.permute(0, 2, 3, 1)) <= 5e-3
 
 
-def _bn_bwd_case(cuda, quad):
+def _bn_bwd_case(cuda, quad, pool=True):
     from fabric_b200 import ops
     torch.manual_seed(6)
     G, B, H, W, C = 2, 2, 13, 10, 64
@@ -165,9 +165,9 @@ def _bn_bwd_case(cuda, quad):
     a_ref = [a.permute(0, 2, 3, 1) for a in acts]
     if quad:   # product fusion relu(d2*d1) (bidate_model.py:35-38) + MaxPool2d (unet_parts.py:40) adjoints
         gcat = torch.randn(1, B, H, W, 2 * C, device=cuda).bfloat16()
-        gp = torch.randn(G, B, H // 2, W // 2, C, device=cuda).bfloat16()
+        gp = torch.randn(G, B, H // 2, W // 2, C, device=cuda).bfloat16() if pool else None
         loss = (gcat[0, ..., :C].float() * torch.relu(a_ref[0] * a_ref[1])).sum()
-        for g in range(G):
+        for g in range(G if pool else 0):
             loss = loss + (gp[g].float().permute(0, 3, 1, 2) * F.max_pool2d(acts[g], 2)).sum()
         loss.backward()
         dz, dg, db = ops.bn_relu_bwd(z, a5, gcat, True, gp, scale, shift, mean.contiguous(), invstd.contiguous(), gam)
@@ -185,6 +185,11 @@ def test_bn_relu_bwd_plain(cuda):
 
 def test_bn_relu_bwd_with_product_and_pool_adjoints(cuda):
     e = _bn_bwd_case(cuda, True)      # the other date's activation enters as a bf16 tensor: looser
+    assert e[0] <= 1.5e-2 and e[1] <= 5e-3 and e[2] <= 5e-3
+
+
+def test_bn_relu_bwd_with_product_only(cuda):
+    e = _bn_bwd_case(cuda, True, pool=False)      # deepest encoder level (down4): product fusion, no pooled consumer
     assert e[0] <= 1.5e-2 and e[1] <= 5e-3 and e[2] <= 5e-3
 
 

@@ -1,4 +1,5 @@
-"""Summarise `ncu --set full` reports (read here, no GPU needed):  python tools/ncu_full_summary.py rep1.ncu-rep ...
+"""Summarise `ncu --set full` reports or their `--page raw --csv` exports (read here, no GPU needed):
+    python tools/ncu_full_summary.py rep1.ncu-rep x.raw.csv ...
 Prints a markdown table of the metrics the roofline discussion uses and a JSON dict of DRAM bytes per launch."""
 import csv
 import io
@@ -16,7 +17,8 @@ out = {}
 print("| report | kernel | " + " | ".join(k for _, k in KEYS) + " |")
 print("|---|---|" + "---|" * len(KEYS))
 for rep in sys.argv[1:]:
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     h, u = rows[0], rows[1]
     for v in rows[2:]:
