@@ -35,10 +35,28 @@ class BiDateNet(nn.Module):
         self.fuse_head = True
         self.fuse_product = True
 
+    def set_input_normalisation(self, mean, std):
+        """Per-band mean / std of the loader's z-score (reference utils/dataloaders.py:94-99, constants in
+        metadata.json:4-29).  With them set, ``forward`` also accepts RAW uint16 rasters [B,13,H,W]: the normalisation runs
+        inside the pack kernel and the host ships half the bytes.  Not part of ``state_dict`` (the reference has no such
+        entry), but the tensors follow ``.to(device)``."""
+        mean = torch.as_tensor(mean, dtype=torch.float32).flatten()
+        std = torch.as_tensor(std, dtype=torch.float32).flatten()
+        dev = next(self.parameters()).device
+        self.register_buffer("_fb_in_mean", mean.to(dev).contiguous(), persistent=False)
+        self.register_buffer("_fb_in_inv_std", (1.0 / std).to(dev).contiguous(), persistent=False)
+
     def pack_pair(self, x_d1, x_d2):
         """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16]."""
         b, c, h, w = x_d1.shape
         x5 = torch.empty((2, b, h, w, ops.cpad(c)), dtype=torch.bfloat16, device=x_d1.device)
+        if x_d1.dtype == torch.uint16:
+            mean, inv_std = getattr(self, "_fb_in_mean", None), getattr(self, "_fb_in_inv_std", None)
+            if mean is None:
+                raise RuntimeError("raw uint16 input needs BiDateNet.set_input_normalisation(mean, std) first")
+            ops.pack_input_raw(x_d1.contiguous(), mean, inv_std, out=x5[0])
+            ops.pack_input_raw(x_d2.contiguous(), mean, inv_std, out=x5[1])
+            return x5
         ops.pack_input(x_d1.contiguous(), out=x5[0])
         ops.pack_input(x_d2.contiguous(), out=x5[1])
         return x5

@@ -23,6 +23,9 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   const int ck = d->Cin == 16 ? 16 : 64;
   int n_tile = d->tune.n_tile;
   if (n_tile == 0) n_tile = d->Cout == 64 ? 64 : (d->Cout % 256 == 0 ? 256 : 128);
+  // product pair without a main output keeps two staging buffers: at 128 wide they leave no room for resident weights
+  // (Cin >= 128), and 64-wide tiles with resident weights measured 10 % faster than 128-wide tiles with streamed ones
+  if (d->tune.n_tile == 0 && d->prod_out && !d->store_main && n_tile == 128 && d->Cin >= 128) n_tile = 64;
   if (!(n_tile == 64 || n_tile == 128 || n_tile == 256) || d->Cout % n_tile)
     return fail(FB_ERR_SHAPE, "n_tile %d does not divide Cout %d", n_tile, d->Cout);
   if (ck == 16 && n_tile != 64) return fail(FB_ERR_SHAPE, "Cin=16 path is built for n_tile 64 only");
@@ -178,15 +181,22 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
 // NCHW fp32 -> NHWC bf16 for the 13-band input (C <= 16, Cpad == 16): one thread = one pixel.  A warp reads 128
 // contiguous bytes per channel plane and writes 1 KB contiguous (one 32-byte st.global.v8 per lane): ~35 instructions
 // per pixel instead of the smem transpose's ~1000 (that kernel was issue-bound at 23 % of HBM bandwidth).
-__global__ void __launch_bounds__(256) pack_nchw16_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, int C,
-                                                          uint32_t hw, uint32_t total) {
+// T = float (z-scored patches as the reference's loader hands them over) or unsigned short (raw Sentinel-2 digital numbers:
+// the per-band z-score of utils/dataloaders.py:94-99 is applied here, so the host ships half the bytes).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_nchw16_kernel(const T* __restrict__ src, uint32_t* __restrict__ dst, int C,
+                                                          uint32_t hw, uint32_t total, const float* __restrict__ mean,
+                                                          const float* __restrict__ inv_std) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= total) return;
   const uint32_t b = i / hw, pos = i - b * hw;
-  const float* s = src + (size_t)b * C * hw + pos;
+  const T* s = src + (size_t)b * C * hw + pos;
   float v[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(s + (size_t)c * hw) : 0.f;
+  for (int c = 0; c < 16; ++c) {
+    v[c] = c < C ? (float)__ldg(s + (size_t)c * hw) : 0.f;
+    if (mean && c < C) v[c] = (v[c] - __ldg(mean + c)) * __ldg(inv_std + c);
+  }
   uint32_t r[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = fb::pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -398,8 +408,8 @@ int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, i
   if (!aligned16(dst)) return fail(FB_ERR_ALIGN, "dst must be 16-byte aligned");
   if (C <= 16 && Cpad == 16 && ((uintptr_t)dst & 31) == 0 && (double)B * H * W < 4.0e9) {
     const uint32_t total = (uint32_t)B * H * W;
-    pack_nchw16_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<uint32_t*>(dst), C,
-                                                                             (uint32_t)H * W, total);
+    pack_nchw16_kernel<float><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<uint32_t*>(dst), C,
+                                                                                    (uint32_t)H * W, total, nullptr, nullptr);
     FB_CUDA(cudaGetLastError());
     return FB_OK;
   }
@@ -409,6 +419,21 @@ int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, i
   if (smem > 48 * 1024) FB_CUDA(cudaFuncSetAttribute(pack_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((W + PX - 1) / PX, H, B);
   pack_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, Cpad, H, W, PX);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_pack_nchw_u16_to_nhwc_bf16(const uint16_t* src, void* dst, const float* mean, const float* inv_std, int B,
+                                           int C, int H, int W, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!src || !dst || !mean || !inv_std) return fail(FB_ERR_ARG, "null pointer");
+  if (C < 1 || C > 16 || B < 1 || H < 1 || W < 1 || (double)B * H * W >= 4.0e9) return fail(FB_ERR_SHAPE, "bad shape");
+  if ((uintptr_t)dst & 31) return fail(FB_ERR_ALIGN, "dst must be 32-byte aligned");
+  const uint32_t total = (uint32_t)B * H * W;
+  pack_nchw16_kernel<unsigned short><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<uint32_t*>(dst), C, (uint32_t)H * W, total, mean, inv_std);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

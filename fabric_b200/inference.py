@@ -21,8 +21,8 @@ class HostPipeline:
         self.copy_in = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
         self.return_logits = return_logits
-        self.bufs = [dict(x1=torch.empty((chunk, n_channels, size, size), device=self.dev),
-                          x2=torch.empty((chunk, n_channels, size, size), device=self.dev),
+        self.shape = (chunk, n_channels, size, size)
+        self.bufs = [dict(x1=torch.empty(self.shape, device=self.dev), x2=torch.empty(self.shape, device=self.dev),
                           ready=torch.cuda.Event(), done=torch.cuda.Event(), out=None, copied=torch.cuda.Event())
                      for _ in range(2)]
 
@@ -31,6 +31,11 @@ class HostPipeline:
         """x*_host: [N,C,S,S] fp32 (pinned for async copies); out_host: [N,2,S,S] fp32 or [N,S,S] uint8 (mask)."""
         n = x1_host.shape[0]
         main = torch.cuda.current_stream(self.dev)
+        if self.bufs[0]["x1"].dtype != x1_host.dtype:   # raw uint16 rasters (model.set_input_normalisation) or fp32 patches
+            main.synchronize()
+            for b in self.bufs:
+                b["x1"] = torch.empty(self.shape, dtype=x1_host.dtype, device=self.dev)
+                b["x2"] = torch.empty(self.shape, dtype=x1_host.dtype, device=self.dev)
         h2d = d2h = 0
         for i, lo in enumerate(range(0, n, self.chunk)):
             hi = min(lo + self.chunk, n)
@@ -41,7 +46,7 @@ class HostPipeline:
                 b["x1"][:k].copy_(x1_host[lo:hi], non_blocking=True)
                 b["x2"][:k].copy_(x2_host[lo:hi], non_blocking=True)
                 b["ready"].record(self.copy_in)
-            h2d += 2 * x1_host[lo:hi].numel() * 4
+            h2d += 2 * x1_host[lo:hi].numel() * x1_host.element_size()
             main.wait_event(b["ready"])
             main.wait_event(b["copied"])                    # previous result of this slot has left the device
             logits = self.model(b["x1"][:k], b["x2"][:k])

@@ -65,6 +65,23 @@ def pack_input(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_pad: Optio
     return out
 
 
+def pack_input_raw(x: torch.Tensor, mean: torch.Tensor, inv_std: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw NCHW uint16 [B,C,H,W] (C <= 16) -> z-scored NHWC bf16 [B,H,W,16]; the normalisation of the reference's loader
+    (utils/dataloaders.py:94-99) runs inside the pack kernel."""
+    _need_cuda(x, mean, inv_std, out)
+    if x.dtype != torch.uint16:
+        raise _lib.FabricB200Error("pack_input_raw expects uint16 rasters")
+    b, c, h, w = x.shape
+    assert mean.dtype == torch.float32 and inv_std.dtype == torch.float32 and mean.numel() == c and inv_std.numel() == c
+    if out is None:
+        out = torch.empty((b, h, w, 16), dtype=torch.bfloat16, device=x.device)
+    assert out.shape == (b, h, w, 16) and out.dtype == torch.bfloat16
+    check(_lib.load().fabric_b200_pack_nchw_u16_to_nhwc_bf16(_p(x), _p(out), _p(mean), _p(inv_std), b, c, h, w, _stream()),
+          "pack_input_raw")
+    _count()
+    return out
+
+
 def unpack_output(x: torch.Tensor) -> torch.Tensor:
     """NHWC bf16 [B,H,W,C] -> NCHW fp32 [B,C,H,W]."""
     _need_cuda(x)

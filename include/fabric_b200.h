@@ -41,6 +41,11 @@ int fabric_b200_sm_count(void);
  * BiDateNet.forward (models/bidate_model.py:22-23,29; inputs come from train.py:83-84). */
 int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, int C, int Cpad, int H, int W,
                                            void* stream);
+/* Raw input: NCHW uint16 [B][C][H][W] (Sentinel-2 digital numbers, C <= 16) -> NHWC bf16 [B][H][W][16] with the per-band
+ * z-score (v - mean[c]) * inv_std[c] of city_loader (utils/dataloaders.py:94-99) applied on the fly, so the host hands
+ * over the rasters as stored (half the bytes of the reference's fp32 patches at train.py:189-190). */
+int fabric_b200_pack_nchw_u16_to_nhwc_bf16(const uint16_t* src, void* dst, const float* mean, const float* inv_std, int B,
+                                           int C, int H, int W, void* stream);
 /* NHWC bf16 [B][H][W][C] -> NCHW fp32 [B][C][H][W] (standalone block outputs / tests). */
 int fabric_b200_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream);
 

@@ -383,3 +383,37 @@ def test_batch_feeder_double_buffer(cuda):
     torch.cuda.synchronize()
     for i, y in enumerate(seen):
         assert float(y) == 2.0 * i * 4 * 13 * 256 + i * 4 * 256
+
+
+def test_raw_uint16_input_matches_oracle_on_normalised_input(cuda):
+    """Raw Sentinel-2 digital numbers in, z-score fused into the pack kernel (reference utils/dataloaders.py:94-99 with the
+    band statistics of metadata.json:4-29) == the oracle fed with the host-normalised fp32 patches."""
+    from fabric_b200 import ops
+    from fabric_b200.inference import HostPipeline
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    model = _model(cuda, sd)
+    mean = torch.tensor([1617.57, 1422.37, 1359.37, 1414.68, 1557.94, 1986.22, 2210.50, 2118.56, 2344.79, 711.84, 15.75,
+                         2133.90, 1584.27])
+    std = torch.tensor([319.12, 456.25, 590.13, 849.37, 811.31, 813.55, 891.85, 901.61, 954.77, 370.95, 9.23, 1116.59, 985.12])
+    g = torch.Generator().manual_seed(5)
+    raw = [(torch.randn(2, 13, 32, 32, generator=g) * std[None, :, None, None] + mean[None, :, None, None])
+           .round().clamp(0, 65535).to(torch.int32).to(torch.uint16) for _ in range(2)]
+    norm = [(r.to(torch.int32).float() - mean[None, :, None, None]) / std[None, :, None, None] for r in raw]   # the loader
+    ref = O.bidatenet_forward(norm[0], norm[1], sd, training=False)
+    model.set_input_normalisation(mean, std)
+    assert "_fb_in_mean" not in model.state_dict()
+    # pack kernel alone: bit-exact against the same arithmetic in torch
+    packed = ops.pack_input_raw(raw[0].to(cuda), model._fb_in_mean, model._fb_in_inv_std)
+    want = ((raw[0].to(torch.int32).float().to(cuda) - model._fb_in_mean[None, :, None, None])
+            * model._fb_in_inv_std[None, :, None, None]).permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(packed[..., :13], want) and bool((packed[..., 13:] == 0).all())
+    with torch.no_grad():
+        out = model(raw[0].to(cuda), raw[1].to(cuda)).cpu()
+    assert ((out - ref).norm() / ref.norm()).item() <= 1e-2
+    # through the host pipeline (pinned uint16 in, logits out)
+    host_out = torch.empty(2, 2, 32, 32).pin_memory()
+    pipe = HostPipeline(model, chunk=2, n_channels=13, size=32, return_logits=True)
+    h2d, _ = pipe.run(raw[0].pin_memory(), raw[1].pin_memory(), host_out)
+    torch.cuda.synchronize()
+    assert h2d == 2 * raw[0].numel() * 2 and torch.equal(host_out, out)
