@@ -31,7 +31,7 @@ class Conv3x3Desc(C.Structure):
         ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("pool_out", C.c_void_p), ("stats_ws", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
-        ("prod_out", C.c_void_p), ("prod_channels", C.c_int),
+        ("prod_out", C.c_void_p), ("prod_channels", C.c_int), ("shift_in_acc", C.c_int),
         ("tune", ConvTuning),
     ]
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "fabric_b200_pack_nchw_u16_to_nhwc_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_pack_conv3x3_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_pack_conv3x3_weight_scaled": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_conv3x3": (_i, [C.POINTER(Conv3x3Desc), _vp]),
     "fabric_b200_conv3x3_grid": (_i, [C.POINTER(Conv3x3Desc)]),
     "fabric_b200_conv3x3_stats_ws_floats": (C.c_int64, [C.POINTER(Conv3x3Desc)]),

@@ -80,6 +80,8 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   const bool n_const = (slots % p.num_n_tiles == 0) || slots == total;
   if (d->stats_ws && slots % p.num_n_tiles != 0 && slots != total)
     return fail(FB_ERR_SHAPE, "stats need a grid that is a multiple of the N tiles");
+  if (d->shift_in_acc && (d->scale || !d->shift)) return fail(FB_ERR_ARG, "shift_in_acc needs shift and no scale");
+  if (d->shift_in_acc && !n_const) return fail(FB_ERR_SHAPE, "shift_in_acc needs one N tile per CTA");
 
   const int a_bytes = fb::conv_a_stage_bytes(ck, halo);
   const int b_bytes = fb::conv_b_stage_bytes(n_tile, ck) / ctas;
@@ -120,7 +122,7 @@ int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   const long long smem = (long long)a_st * a_bytes + (long long)b_st * b_bytes + fixed;
   if (smem > di.smem_optin) return fail(FB_ERR_SHAPE, "shared memory %lld > %d", smem, di.smem_optin);
   p.a_stages = a_st, p.b_stages = b_st, p.b_resident = b_res;
-  p.relu = d->relu, p.store_main = d->store_main;
+  p.relu = d->relu, p.store_main = d->store_main, p.acc_init = d->shift_in_acc ? 1 : 0;
   p.scale = d->scale, p.shift = d->shift;
   p.pool_out = reinterpret_cast<__nv_bfloat16*>(d->pool_out);
   p.stats_out = d->stats_ws;
@@ -219,14 +221,14 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ src, float*
   }
 }
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
-                                   int CinPad, int mode) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, __nv_bfloat16* __restrict__ dst,
+                                   int Cout, int Cin, int CinPad, int mode) {
   const size_t n = mode == 0 ? (size_t)Cout * 9 * CinPad : (size_t)Cin * 9 * Cout;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = 0.f;
     if (mode == 0) {
       const int ci = i % CinPad, tap = (i / CinPad) % 9, co = i / ((size_t)CinPad * 9);
-      if (ci < Cin) v = w[((size_t)co * Cin + ci) * 9 + tap];
+      if (ci < Cin) v = w[((size_t)co * Cin + ci) * 9 + tap] * (scale ? scale[co] : 1.f);
     } else {
       const int co = i % Cout, tap = (i / Cout) % 9, ci = i / ((size_t)Cout * 9);
       v = w[((size_t)co * Cin + ci) * 9 + (8 - tap)];
@@ -453,15 +455,21 @@ int fabric_b200_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B,
 }
 
 int fabric_b200_pack_conv3x3_weight(const float* w, void* dst, int Cout, int Cin, int CinPad, int mode, void* stream) {
+  return fabric_b200_pack_conv3x3_weight_scaled(w, nullptr, dst, Cout, Cin, CinPad, mode, stream);
+}
+
+int fabric_b200_pack_conv3x3_weight_scaled(const float* w, const float* scale, void* dst, int Cout, int Cin, int CinPad, int mode,
+                                           void* stream) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   if (!w || !dst) return fail(FB_ERR_ARG, "null pointer");
   if (mode != 0 && mode != 1) return fail(FB_ERR_ARG, "mode must be 0 or 1");
+  if (scale && mode != 0) return fail(FB_ERR_ARG, "per-output-channel scale is for forward weights (mode 0)");
   if (Cout < 1 || Cin < 1 || CinPad < Cin || (mode == 1 && CinPad != Cin)) return fail(FB_ERR_SHAPE, "bad shape");
   const size_t n = mode == 0 ? (size_t)Cout * 9 * CinPad : (size_t)Cin * 9 * Cout;
   pack_weight_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(dst), Cout, Cin, CinPad, mode);
+      w, scale, reinterpret_cast<__nv_bfloat16*>(dst), Cout, Cin, CinPad, mode);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

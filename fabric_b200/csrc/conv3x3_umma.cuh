@@ -32,6 +32,8 @@ struct Conv3x3Params {
   int a_stages, b_stages;
   int b_resident;  // weights for this CTA's N tile stay in smem for the whole kernel
   int relu;
+  int acc_init;  // the accumulator starts at `shift` (written to TMEM by the epilogue warps) instead of zero: with the
+                 // BatchNorm scale folded into the weights the epilogue is convert + store, no per-element affine
   int store_main;
   const float* scale;  // per out channel, nullable (=1)
   const float* shift;  // per out channel, nullable (=0)
@@ -343,10 +345,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     TileCoord tc_unused;
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, 0, tc_unused); ++tile_it) {
       const int acc = tile_it & 1;
-      mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ 1);
+      // (acc_init: even the first use of a buffer waits for the epilogue warps, which preload it with the shift)
+      mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ (p.acc_init ? 0u : 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
-      uint32_t accumulate = 0;
+      uint32_t accumulate = p.acc_init ? 1u : 0u;
       for (int c = 0; c < p.kchunks; ++c) {
         const bool last_chunk = (c == p.kchunks - 1);
         if constexpr (TAPS_PER_A == 9) {
@@ -464,15 +467,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int pn = (m >> 3) / p.bh;
     // this warp's 4 tile rows (32 pixels) as a TMA store box: rows [wy, wy + min(bh,4)) of images [wn, ...)
     const int wn = (q * 4) / p.bh, wy = (q * 4) % p.bh;
-    const bool affine = p.scale != nullptr || p.shift != nullptr;
+    const bool affine = !p.acc_init && (p.scale != nullptr || p.shift != nullptr);
     const bool relu = p.relu != 0;
     const bool extras = p.stats_out || p.pool_out || p.prod_out || p.head_out;   // one branch for the common plain tile
     // epilogue options as ONE opaque register: the chunk loop tests bits instead of re-reading kernel parameters through
     // the constant bank (LDCU + ISETP + BRA per test, each a latency bubble with one or two warps per scheduler)
-    enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128 };
+    enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128,
+                      F_INIT = 256 };
     uint32_t flags = (p.store_main ? F_MAIN : 0u) | (p.prod_out ? F_PROD : 0u) | (p.stats_out ? F_STATS : 0u) |
                      (p.pool_out ? F_POOL : 0u) | (p.pool_tma ? F_POOL_TMA : 0u) | (p.prod_tma ? F_PROD_TMA : 0u) |
-                     (p.head_out ? F_HEAD : 0u) | (p.out_bufs == 2 ? F_TWO : 0u);
+                     (p.head_out ? F_HEAD : 0u) | (p.out_bufs == 2 ? F_TWO : 0u) | (p.acc_init ? F_INIT : 0u);
     asm volatile("mov.b32 %0, %0;" : "+r"(flags));
     const int pH = p.H, pW = p.W, pB = p.B, pCout = p.Cout, pCt = p.prod_ct;
     int cur_n0 = -1;
@@ -487,6 +491,40 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* hx = ss + 2 * N_TILE + 136;   // [128][2] head partial sums handed from warp group 1 to group 0 (EW = 8)
     bar_sync(1, kEpiThreads);   // stats / head constants visible; the ONLY CTA-wide epilogue barrier in steady state
     TileCoord tc;
+    // this warp's 32 accumulator columns of chunk cc <- shift[n0 + cc*32 ..] in every lane (pixel row)
+    auto preload_shift = [&](int acc_, int cc) {
+      uint32_t sv[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 sh = *reinterpret_cast<const float4*>(ss + N_TILE + cc * 32 + j);
+        sv[j] = __float_as_uint(sh.x), sv[j + 1] = __float_as_uint(sh.y), sv[j + 2] = __float_as_uint(sh.z),
+        sv[j + 3] = __float_as_uint(sh.w);
+      }
+      tmem_st_32x32(tmem_base + acc_ * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), sv);
+    };
+    if ((flags & F_INIT) && tile_at<CTAS>(p, 0, N_TILE, rank, tc)) {
+      // (the planner guarantees one N tile per CTA in this mode, so the shift vector is loaded once)
+      for (int i = etid; i < N_TILE; i += kEpiThreads) {
+        ss[i] = 1.f;
+        ss[N_TILE + i] = p.shift[tc.n0 + i];
+      }
+      cur_n0 = tc.n0;
+      bar_sync(1, kEpiThreads);
+      for (int cc = eg; cc < NCHUNK; cc += kEpiGroups) {
+        preload_shift(0, cc);
+        preload_shift(1, cc);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int a_ = 0; a_ < 2; ++a_) {
+          if (CTAS == 2) mbar_arrive_cluster(on_leader(tmem_empty(a_)));
+          else mbar_arrive(tmem_empty(a_));
+        }
+      }
+    }
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, rank, tc); ++tile_it) {
       const int acc = tile_it & 1;
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
@@ -521,22 +559,31 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
+        if (flags & F_INIT) preload_shift(acc, cc);   // the buffer's next tile starts from the shift again
         uint32_t pk[16];
         if (affine) {
+          float v[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 sc = *reinterpret_cast<const float4*>(ss + cc * 32 + j);
             const float4 sh = *reinterpret_cast<const float4*>(ss + N_TILE + cc * 32 + j);
-            pk[j / 2] = pack_bf16x2(fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x), fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
-            pk[j / 2 + 1] = pack_bf16x2(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
+            v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x), v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+            v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
           }
+          // ReLU rides in the conversion (cvt.rn.relu.bf16x2.f32): relu(round(x)) == round(relu(x))
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+        } else if (relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         } else {  // raw accumulator (training forward before BatchNorm, data gradient)
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        }
-        if (relu) {  // on the packed pair: relu(round(x)) == round(relu(x))
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = bf16x2_max(pk[j], 0u);
         }
 
         // staging for the TMA store: sub-tile (cc/2) of 64 channels, row m, 16-byte chunk index XOR (m & 7)
@@ -624,7 +671,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         }  // extras
       }
-      // accumulator drained -> MMA may overwrite it
+      // accumulator drained (and re-primed) -> MMA may overwrite it
+      if (flags & F_INIT) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -92,9 +92,11 @@ def unpack_output(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def pack_conv_weight(w: torch.Tensor, mode: int = 0) -> torch.Tensor:
-    """[Cout,Cin,3,3] fp32 -> bf16 [Cout,9,CinPad] (mode 0, forward) or [Cin,9,Cout] with flipped taps (mode 1, dgrad)."""
-    _need_cuda(w)
+def pack_conv_weight(w: torch.Tensor, mode: int = 0, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[Cout,Cin,3,3] fp32 -> bf16 [Cout,9,CinPad] (mode 0, forward) or [Cin,9,Cout] with flipped taps (mode 1, dgrad).
+    ``scale`` [Cout] fp32 (mode 0 only) multiplies each output channel's filter before rounding: the eval-mode BatchNorm
+    scale folded into the weights (see ``conv3x3(..., shift_in_acc=True)``)."""
+    _need_cuda(w, scale)
     w = w.detach()
     if w.dtype != torch.float32:
         w = w.float()
@@ -105,7 +107,8 @@ def pack_conv_weight(w: torch.Tensor, mode: int = 0) -> torch.Tensor:
     else:
         cp = cin
         out = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=w.device)
-    check(_lib.load().fabric_b200_pack_conv3x3_weight(_p(w), _p(out), cout, cin, cp, mode, _stream()), "pack_conv_weight")
+    check(_lib.load().fabric_b200_pack_conv3x3_weight_scaled(_p(w), _p(scale), _p(out), cout, cin, cp, mode, _stream()),
+          "pack_conv_weight")
     _count()
     return out
 
@@ -133,7 +136,7 @@ DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, 
 def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False, pool: bool = False, stats: bool = False,
             head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None,
-            true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None):
+            true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None, shift_in_acc: bool = False):
     """3x3 pad-1 convolution on tcgen05 (see include/fabric_b200.h: fabric_b200_conv3x3).
 
     Returns a dict with ``y`` [G,B,H,W,cout] bf16 and optionally ``pool`` [G,B,H/2,W/2,cout],
@@ -145,7 +148,7 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
     g, b, h, w, cin = x5.shape
     d = Conv3x3Desc()
     d.G, d.B, d.H, d.W, d.Cin, d.Cout = g, b, h, w, cin, cout
-    d.relu, d.store_main = int(relu), int(store_main)
+    d.relu, d.store_main, d.shift_in_acc = int(relu), int(store_main), int(shift_in_acc)
     t = dict(DEFAULT_TUNING)
     if tune:
         t.update(tune)

@@ -52,6 +52,9 @@ class double_conv(nn.Module):
         self.in_ch, self.out_ch = in_ch, out_ch
         self.tune1 = None   # optional fb_conv_tuning overrides (dict), used by the benchmarks
         self.tune2 = None
+        # eval mode: fold the BatchNorm scale into the packed weights and start the accumulator at the shift, so the conv
+        # epilogue is convert + ReLU + store (False = per-element scale / shift in the epilogue, one packed copy for all)
+        self.fold_bn = True
 
     # caches are not part of the module state (and must not be pickled)
     def _cache(self) -> _PackCache:
@@ -75,12 +78,28 @@ class double_conv(nn.Module):
         return self._cache().get(("bn", idx), [bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.bias],
                                  lambda: ops.bn_fold_eval(bn, conv.bias), extra=bn.__dict__.get("_fb_stats_epoch", 0))
 
+    def _packed_folded(self, idx):
+        """(bf16 weights with the eval BatchNorm scale folded in, shift) for conv ``idx``."""
+        conv, bn = self.conv[idx], self.conv[idx + 1]
+        scale, shift = self._folded(idx)
+        w = self._cache().get(("w_folded", idx), [conv.weight, bn.weight, bn.running_var],
+                              lambda: ops.pack_conv_weight(conv.weight, 0, scale=scale),
+                              extra=bn.__dict__.get("_fb_stats_epoch", 0))
+        return w, shift
+
     def run5(self, x5, pool=False, head=None, keep_main=True, prod_out=None):
         """NHWC5 bf16 in -> dict(y=..., pool=..., logits=...).  Eval mode: BatchNorm (running statistics), the conv
         bias and ReLU ride in the conv epilogue; ``pool`` adds the fused MaxPool2d(2) copy for the next ``down``;
         ``head`` = (weight[2,64], bias[2]) fuses ``outconv`` into the second conv."""
         if self.training:
             raise NotImplementedError("training-mode forward goes through fabric_b200.autograd (double_conv_train)")
+        if getattr(self, "fold_bn", True):
+            w1, h1 = self._packed_folded(0)
+            w2, h2 = self._packed_folded(3)
+            mid = ops.conv3x3(x5, w1, self.out_ch, None, h1, relu=True, tune=self.tune1, true_cin=self.in_ch,
+                              shift_in_acc=True)["y"]
+            return ops.conv3x3(mid, w2, self.out_ch, None, h2, relu=True, pool=pool, head=head, store_main=keep_main,
+                               tune=self.tune2, prod_out=prod_out, shift_in_acc=True)
         s1, h1 = self._folded(0)
         s2, h2 = self._folded(3)
         mid = ops.conv3x3(x5, self._packed(0), self.out_ch, s1, h1, relu=True, tune=self.tune1, true_cin=self.in_ch)["y"]

@@ -53,6 +53,10 @@ int fabric_b200_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B,
  *   mode 0 (forward): dst[Cout][9][CinPad], k = tap*CinPad + ci, tap = ky*3+kx
  *   mode 1 (dgrad)  : dst[Cin][9][Cout],    taps flipped, so that dX = conv3x3(dY, dst)            */
 int fabric_b200_pack_conv3x3_weight(const float* w, void* dst, int Cout, int Cin, int CinPad, int mode, void* stream);
+/* mode 0 with w[co] * scale[co] (scale fp32 [Cout], nullable): eval-mode BatchNorm scale folded into the weights, used
+ * together with fb_conv3x3_desc.shift_in_acc */
+int fabric_b200_pack_conv3x3_weight_scaled(const float* w, const float* scale, void* dst, int Cout, int Cin, int CinPad,
+                                           int mode, void* stream);
 
 /* ---- 3x3 convolution (tcgen05 implicit GEMM) ---------------------------------------------------------------- */
 
@@ -87,6 +91,8 @@ typedef struct {
   void* prod_out;      /* NULL or bf16 [B][H][W][prod_channels]: fused relu(y[date 1] * y[date 0]) written into
                           channels [0, Cout) -- the skip half of the decoder input (bidate_model.py:35-38); G == 2 */
   int prod_channels;
+  int shift_in_acc;    /* 1: the accumulator starts at shift[] (scale must be NULL, i.e. folded into w): y = acc + shift.
+                          The epilogue is then convert (+ReLU) + store; the epilogue warps re-prime TMEM after each tile */
   fb_conv_tuning tune;
 } fb_conv3x3_desc;
 

@@ -85,6 +85,36 @@ def test_conv3x3_matches_oracle(cuda, G, B, H, W, cin, cout, tune):
     assert (y - ref).abs().max() <= 2 ** -7 * ref.abs().max() + 1e-6
 
 
+@pytest.mark.parametrize("G,B,H,W,cin,cout,tune", CONV_CASES)
+def test_conv3x3_folded_scale_and_shift_in_accumulator(cuda, G, B, H, W, cin, cout, tune):
+    """Eval-mode form: BatchNorm scale folded into the packed weights, accumulator primed with the shift (TMEM preload by
+    the epilogue warps): same result as the per-element affine epilogue up to the bf16 rounding of w * scale."""
+    from fabric_b200 import ops
+    torch.manual_seed(G * 1000 + H * 10 + cin + 1)
+    cp = ops.cpad(cin)
+    x5 = torch.zeros(G, B, H, W, cp, device=cuda, dtype=torch.bfloat16)
+    x5[..., :cin] = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
+    w = torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5)
+    scale = 0.5 + torch.rand(cout, device=cuda)
+    shift = 0.3 * torch.randn(cout, device=cuda)
+    wf = ops.pack_conv_weight(w, 0, scale=scale)
+    assert torch.equal(wf[..., :cin], (w * scale[:, None, None, None]).permute(0, 2, 3, 1).reshape(cout, 9, cin).bfloat16())
+    kw = dict(pool=True) if (H % 2 == 0 and W % 2 == 0 and H > 1) else {}
+    res = ops.conv3x3(x5, wf, cout, None, shift, relu=True, tune=tune, shift_in_acc=True, **kw)
+    y = res["y"].reshape(G * B, H, W, cout).permute(0, 3, 1, 2).float().cpu()
+    x = x5.reshape(G * B, H, W, cp)[..., :cin].permute(0, 3, 1, 2).float().cpu()
+    ref = (F.conv2d(x, (w * scale[:, None, None, None]).bfloat16().float().cpu(), None, padding=1)
+           + shift.cpu()[None, :, None, None]).relu()
+    assert rel(y, ref) < CONV_TOL
+    assert (y - ref).abs().max() <= 2 ** -7 * ref.abs().max() + 1e-6
+    if kw:
+        assert torch.equal(res["pool"].reshape(G * B, H // 2, W // 2, cout).permute(0, 3, 1, 2).float().cpu(),
+                           F.max_pool2d(y, 2))
+    # twice in a row on the same stream: the re-primed accumulators of the first launch must not leak into the second
+    res2 = ops.conv3x3(x5, wf, cout, None, shift, relu=True, tune=tune, shift_in_acc=True)
+    assert torch.equal(res2["y"], res["y"])
+
+
 @pytest.mark.parametrize("halo", [0, 1])
 def test_conv3x3_fused_pool_stats_head(cuda, halo):
     from fabric_b200 import ops
