@@ -36,6 +36,11 @@ class Conv3x3Desc(C.Structure):
     ]
 
 
+class ConvPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_tile", "ck", "halo", "grid", "smem_bytes", "ctas", "epi_warps", "a_stages",
+                                       "b_stages", "b_resident", "out_bufs", "total_units", "pool_tma", "prod_tma")]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("G", C.c_int), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ca", C.c_int), ("Cb", C.c_int),
                 ("p", C.c_void_p), ("q", C.c_void_p), ("ws", C.c_void_p), ("splits", C.c_int), ("wide", C.c_int)]
@@ -53,6 +58,7 @@ SIGNATURES = {
     "fabric_b200_pack_conv3x3_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_pack_conv3x3_weight_scaled": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_conv3x3": (_i, [C.POINTER(Conv3x3Desc), _vp]),
+    "fabric_b200_conv3x3_plan": (_i, [C.POINTER(Conv3x3Desc), _i, _i, C.POINTER(ConvPlan)]),
     "fabric_b200_conv3x3_grid": (_i, [C.POINTER(Conv3x3Desc)]),
     "fabric_b200_conv3x3_stats_ws_floats": (C.c_int64, [C.POINTER(Conv3x3Desc)]),
     "fabric_b200_bn_fold_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp]),

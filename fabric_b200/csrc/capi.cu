@@ -12,11 +12,19 @@ struct ConvPlan {
   int n_tile, ck, halo, grid, smem, ctas, ew;
 };
 
+int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di);
+
 int plan_conv(const fb_conv3x3_desc* d, ConvPlan* pl) {
   if (!d) return fail(FB_ERR_ARG, "null descriptor");
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
+  return plan_conv_on(d, pl, di);
+}
+
+// the launch plan as a pure function of the descriptor and the device limits (no CUDA calls: testable without a GPU)
+int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
+  if (!d) return fail(FB_ERR_ARG, "null descriptor");
   if (d->G < 1 || d->G > 2 || d->B < 1 || d->H < 1 || d->W < 1) return fail(FB_ERR_SHAPE, "bad G/B/H/W");
   if (!(d->Cin == 16 || (d->Cin > 0 && d->Cin % 64 == 0))) return fail(FB_ERR_SHAPE, "Cin %d must be 16 or k*64", d->Cin);
   if (d->Cout <= 0 || d->Cout % 64) return fail(FB_ERR_SHAPE, "Cout %d must be a multiple of 64", d->Cout);
@@ -471,6 +479,20 @@ int fabric_b200_pack_conv3x3_weight_scaled(const float* w, const float* scale, v
   pack_weight_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       w, scale, reinterpret_cast<__nv_bfloat16*>(dst), Cout, Cin, CinPad, mode);
   FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, fb_conv3x3_plan* out) {
+  if (!d || !out) return fail(FB_ERR_ARG, "null pointer");
+  DeviceInfo di;
+  di.ok = 1, di.sms = sms, di.smem_optin = smem_optin;
+  ConvPlan pl;
+  int rc = plan_conv_on(d, &pl, di);
+  if (rc) return rc;
+  out->n_tile = pl.n_tile, out->ck = pl.ck, out->halo = pl.halo, out->grid = pl.grid, out->smem_bytes = pl.smem;
+  out->ctas = pl.ctas, out->epi_warps = pl.ew, out->a_stages = pl.p.a_stages, out->b_stages = pl.p.b_stages;
+  out->b_resident = pl.p.b_resident, out->out_bufs = pl.p.out_bufs, out->total_units = pl.p.total_units;
+  out->pool_tma = pl.p.pool_tma, out->prod_tma = pl.p.prod_tma;
   return FB_OK;
 }
 

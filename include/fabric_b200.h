@@ -100,6 +100,13 @@ typedef struct {
  * Replaces nn.Conv2d(in,out,3,padding=1) and the BatchNorm2d(eval)/ReLU that follow it
  * (models/unet_parts.py:13-18); with mode-1 weights it is also the data gradient of that conv. */
 int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream);
+/* The launch plan fabric_b200_conv3x3 would use on a device with `sms` SMs and `smem_optin` bytes of opt-in shared memory
+ * per block (B200: 148, 232448).  Pure host arithmetic, no CUDA call: pointers in `d` only need to be NULL / non-NULL. */
+typedef struct {
+  int n_tile, ck, halo, grid, smem_bytes, ctas, epi_warps, a_stages, b_stages, b_resident, out_bufs, total_units;
+  int pool_tma, prod_tma;
+} fb_conv3x3_plan;
+int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, fb_conv3x3_plan* out);
 /* grid the launch above will use, and the stats workspace size (floats) for it */
 int fabric_b200_conv3x3_grid(const fb_conv3x3_desc* d);
 int64_t fabric_b200_conv3x3_stats_ws_floats(const fb_conv3x3_desc* d);

@@ -1,0 +1,108 @@
+"""CPU: the conv launch planner (pure host arithmetic behind fabric_b200_conv3x3_plan) on every BiDateNet layer shape of
+BASELINE configs 2-4 (64 pairs of 13x256x256) and on the ragged shapes of the GPU parity tests: shared memory fits the
+B200 limit, persistent slots cover the work, CTA pairs / resident weights / epilogue warps are chosen as DESIGN.md says."""
+import ctypes as C
+
+import pytest
+
+SMS, SMEM = 148, 232448          # B200: SM count, opt-in shared memory per block
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    return built_lib
+
+
+def plan(lib, G, B, H, W, cin, cout, **kw):
+    from fabric_b200 import _lib
+    d = _lib.Conv3x3Desc()
+    d.G, d.B, d.H, d.W, d.Cin, d.Cout = G, B, H, W, (16 if cin <= 16 else cin), cout
+    d.relu, d.store_main = 1, int(kw.get("store_main", 1))
+    d.x = d.w = 0x1000
+    d.y = 0x1000 if d.store_main else None
+    for k in ("pool_out", "stats_ws", "prod_out", "head_out", "head_w", "head_b", "shift", "scale"):
+        if kw.get(k):
+            setattr(d, k, 0x1000)
+    d.prod_channels = kw.get("prod_channels", 0)
+    d.shift_in_acc = int(kw.get("shift_in_acc", 0))
+    d.tune = _lib.ConvTuning(kw.get("n_tile", 0), -1, 0, 0, -1, 0, kw.get("ctas", 0), kw.get("epi_warps", 0))
+    out = _lib.ConvPlan()
+    rc = lib.fabric_b200_conv3x3_plan(C.byref(d), SMS, SMEM, C.byref(out))
+    return rc, out
+
+
+# name, G, H, cin, cout  (B = 64 pairs)
+LAYERS = [("inc.c1", 2, 256, 13, 64), ("inc.c2", 2, 256, 64, 64), ("down1.c1", 2, 128, 64, 128), ("down1.c2", 2, 128, 128, 128),
+          ("down2.c1", 2, 64, 128, 256), ("down2.c2", 2, 64, 256, 256), ("down3.c1", 2, 32, 256, 512),
+          ("down3.c2", 2, 32, 512, 512), ("down4.c1", 2, 16, 512, 512), ("up1.c1", 1, 32, 1024, 256), ("up1.c2", 1, 32, 256, 256),
+          ("up2.c1", 1, 64, 512, 128), ("up2.c2", 1, 64, 128, 128), ("up3.c1", 1, 128, 256, 64), ("up3.c2", 1, 128, 64, 64),
+          ("up4.c1", 1, 256, 128, 64), ("up4.c2", 1, 256, 64, 64)]
+
+
+@pytest.mark.parametrize("name,G,H,cin,cout", LAYERS)
+@pytest.mark.parametrize("mode", ["eval", "train_fwd", "dgrad"])
+def test_every_layer_has_a_valid_pair_plan(lib, name, G, H, cin, cout, mode):
+    kw = {}
+    if mode == "eval":
+        kw = dict(shift=1, shift_in_acc=1)
+    elif mode == "train_fwd":
+        kw = dict(stats_ws=1)
+    else:
+        if cin == 13:
+            pytest.skip("the stem needs no data gradient")
+        cin, cout = cout, cin           # the data gradient is the same kernel with the channel roles swapped
+    rc, p = plan(lib, G, 64, H, H, cin, cout, **kw)
+    assert rc == 0, lib.fabric_b200_last_error()
+    assert p.smem_bytes <= SMEM
+    assert p.ctas == 2 and p.grid % 2 == 0 and p.grid <= SMS          # CTA pairs on every real layer
+    assert p.n_tile == (64 if cout == 64 else 256 if cout % 256 == 0 else 128)
+    assert p.epi_warps == (8 if p.n_tile <= 128 else 4)
+    assert p.a_stages >= 2 and p.b_stages >= 1
+    n_tiles = cout // p.n_tile
+    assert (p.grid // 2) % n_tiles == 0                                # each CTA keeps one N tile
+    m_tiles = G * 64 * (H // 16 if H >= 16 else 1) * (H // 8)
+    assert p.total_units == m_tiles // 2 * n_tiles
+    # resident weights: always for the small slabs, and then the slab is exactly 9 * Cin / CK stages
+    cin_p = 16 if cin <= 16 else cin
+    if cin_p * p.n_tile <= 128 * 64:
+        assert p.b_resident == 1
+    if p.b_resident:
+        assert p.b_stages == 9 * (cin_p // p.ck)
+        a_stage = 23552 if p.ck == 64 else 6144                                # halo tile: 18 x 10 pixels x CK channels
+        assert 9 * cin_p * p.n_tile + p.a_stages * a_stage <= p.smem_bytes     # half the N tile per CTA of the pair
+    if name == "down1.c2" and mode == "eval":
+        assert p.b_resident == 1                                               # the 147 KB slab fits next to two input stages
+
+
+def test_lean_eval_encoder_levels(lib):
+    # inc.c2 / down1.c2 in eval: pooled copy + product, no full-resolution output, two staging buffers, both through TMA
+    rc, p = plan(lib, 2, 64, 256, 256, 64, 64, pool_out=1, prod_out=1, prod_channels=128, store_main=0, shift=1, shift_in_acc=1)
+    assert rc == 0 and p.out_bufs == 2 and p.pool_tma == 1 and p.prod_tma == 1 and p.b_resident == 1 and p.smem_bytes <= SMEM
+    rc, p = plan(lib, 2, 64, 128, 128, 128, 128, pool_out=1, prod_out=1, prod_channels=256, store_main=0, shift=1, shift_in_acc=1)
+    assert rc == 0 and p.n_tile == 64 and p.b_resident == 1 and p.out_bufs == 2 and p.smem_bytes <= SMEM
+    # 256 wide: single buffer, product through L2, main output required
+    rc, p = plan(lib, 2, 64, 64, 64, 256, 256, pool_out=1, prod_out=1, prod_channels=512, store_main=1)
+    assert rc == 0 and p.out_bufs == 1 and p.prod_tma == 0 and p.pool_tma == 1
+    rc, _ = plan(lib, 2, 64, 64, 64, 256, 256, pool_out=1, prod_out=1, prod_channels=512, store_main=0)
+    assert rc != 0
+
+
+@pytest.mark.parametrize("G,B,H,W,cin,cout", [(1, 1, 16, 8, 64, 64), (2, 3, 20, 12, 64, 64), (1, 3, 45, 45, 13, 64),
+                                              (2, 5, 2, 2, 128, 128), (1, 1, 1, 1, 64, 64), (2, 2, 5, 5, 64, 64)])
+def test_ragged_shapes_plan(lib, G, B, H, W, cin, cout):
+    rc, p = plan(lib, G, B, H, W, cin, cout)
+    assert rc == 0, lib.fabric_b200_last_error()
+    assert p.smem_bytes <= SMEM and p.grid >= 1 and p.total_units >= 1
+    bh = 16 if H > 8 else 8 if H > 4 else 4 if H > 2 else 2
+    m_tiles = G * ((B + 16 // bh - 1) // (16 // bh)) * ((H + bh - 1) // bh) * ((W + 7) // 8)
+    assert p.ctas == (2 if m_tiles % 2 == 0 else 1)                    # an odd number of pixel tiles cannot be paired
+    assert p.total_units == m_tiles // p.ctas * (cout // p.n_tile)
+
+
+def test_bad_requests_are_refused(lib):
+    assert plan(lib, 1, 1, 16, 16, 48, 64)[0] != 0                      # Cin not 16 / k*64
+    assert plan(lib, 1, 1, 16, 16, 64, 96)[0] != 0                      # Cout not a multiple of 64
+    assert plan(lib, 1, 2, 16, 16, 64, 64, ctas=2)[0] == 0
+    assert plan(lib, 1, 1, 16, 8, 64, 64, ctas=2)[0] != 0               # a single pixel tile cannot form a pair
+    assert plan(lib, 1, 2, 16, 16, 64, 256, epi_warps=8)[0] != 0        # 8 epilogue warps only up to 128-wide tiles
+    assert plan(lib, 1, 2, 16, 16, 64, 64, shift_in_acc=1)[0] != 0      # needs the shift vector
