@@ -20,7 +20,7 @@ class FabricB200Error(RuntimeError):
 
 class ConvTuning(C.Structure):
     _fields_ = [("n_tile", C.c_int), ("halo", C.c_int), ("a_stages", C.c_int), ("b_stages", C.c_int),
-                ("b_resident", C.c_int), ("grid", C.c_int), ("ctas", C.c_int), ("epi_warps", C.c_int)]
+                ("b_resident", C.c_int), ("grid", C.c_int), ("ctas", C.c_int), ("epi_warps", C.c_int), ("occupancy", C.c_int)]
 
 
 class Conv3x3Desc(C.Structure):
@@ -38,7 +38,7 @@ class Conv3x3Desc(C.Structure):
 
 class ConvPlan(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_tile", "ck", "halo", "grid", "smem_bytes", "ctas", "epi_warps", "a_stages",
-                                       "b_stages", "b_resident", "out_bufs", "total_units", "pool_tma", "prod_tma")]
+                                       "b_stages", "b_resident", "out_bufs", "total_units", "pool_tma", "prod_tma", "ctas_per_sm")]
 
 
 class WgradDesc(C.Structure):

@@ -9,7 +9,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------ conv planning
 struct ConvPlan {
   fb::Conv3x3Params p;
-  int n_tile, ck, halo, grid, smem, ctas, ew;
+  int n_tile, ck, halo, grid, smem, ctas, ew, minb;
 };
 
 int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di);
@@ -65,14 +65,24 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   if (halo && !halo_ok) return fail(FB_ERR_SHAPE, "halo mode needs H > 8");
 
   // epilogue warps: 8 (two per TMEM lane quarter) for the 64- and 128-wide tiles, whose epilogue is the bottleneck
+  // The 13-band stem (9 MMAs per tile) is bound by the per-tile latency chain of its epilogue, not by any pipe: two CTAs
+  // per SM with four epilogue warps each (two independent tile pipelines) measured 0.32 ms against 0.43 ms for one CTA
+  // with eight; every other shape lost (their resident weights / stage counts do not fit twice).
+  const bool stem_auto = ck == 16 && d->tune.occupancy == 0 && d->tune.epi_warps == 0;
   int ew = d->tune.epi_warps;
-  if (ew == 0) ew = n_tile <= 128 ? 8 : 4;
+  if (ew == 0) ew = stem_auto ? 4 : (n_tile <= 128 ? 8 : 4);
   if (!(ew == 4 || (ew == 8 && n_tile <= 128))) return fail(FB_ERR_ARG, "tune.epi_warps must be 0, 4 or (n_tile <= 128) 8");
+  // CTAs per SM: 2 only on request, for 64-wide tiles with four epilogue warps
+  const int minb = (d->tune.occupancy == 2 || stem_auto) ? 2 : 1;
+  if (d->tune.occupancy < 0 || d->tune.occupancy > 2) return fail(FB_ERR_ARG, "tune.occupancy must be 0, 1 or 2");
+  if (minb == 2 && (n_tile != 64 || ew != 4)) return fail(FB_ERR_ARG, "two CTAs per SM need n_tile 64 and 4 epilogue warps");
+  const int smem_cap = minb == 2 ? 112 * 1024 : di.smem_optin;
+  const int sm_slots = di.sms * minb;
   // CTA pairs (cta_group::2): two adjacent M tiles share one M = 256 MMA and each CTA stages half of the weight rows.
   // Needs an even number of M tiles per date-pair unit and room for at least one pair per N tile.
   const int m_units = p.num_m_tiles / (d->prod_out ? 2 : 1);   // M tiles the persistent loop enumerates
   int ctas = d->tune.ctas;
-  const bool pair_ok = (m_units % 2 == 0) && di.sms >= 2 * p.num_n_tiles;
+  const bool pair_ok = (m_units % 2 == 0) && sm_slots >= 2 * p.num_n_tiles;
   if (ctas == 0) ctas = pair_ok ? 2 : 1;
   if (ctas != 1 && ctas != 2) return fail(FB_ERR_ARG, "tune.ctas must be 0 (auto), 1 or 2");
   if (ctas == 2 && !pair_ok) return fail(FB_ERR_SHAPE, "CTA pairs need an even number of M tiles (%d)", m_units);
@@ -80,7 +90,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   // slots = CTAs or CTA pairs
   const long long total = (long long)(m_units / ctas) * p.num_n_tiles;
   p.total_units = (int)total;
-  int slots = (d->tune.grid > 0 ? d->tune.grid : di.sms) / ctas;
+  int slots = (d->tune.grid > 0 ? d->tune.grid : sm_slots) / ctas;
   if (slots > total) slots = (int)total;
   else slots = (slots / p.num_n_tiles) * p.num_n_tiles;  // each CTA keeps one N tile for its whole life
   if (slots < 1) slots = (int)(total < p.num_n_tiles ? total : p.num_n_tiles);
@@ -102,7 +112,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   const int prod_tma = (d->prod_out && out_bufs == 2 && !d->store_main) ? 1 : 0;
   const int fixed = out_bufs * 128 * n_tile * 2 + (pool_tma ? out_bufs * 4 * (n_tile / 64) * 1024 : 0) +
                     fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr) + 1024;
-  const int avail = di.smem_optin - fixed;
+  const int avail = smem_cap - fixed;
   const int kblocks = 9 * p.kchunks;
   int b_res = d->tune.b_resident;
   const bool res_fits = n_const && (slots % p.num_n_tiles == 0 || p.num_n_tiles == 1 || slots == total) &&
@@ -128,7 +138,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   }
   if (a_st < 1 || b_st < 1 || a_st > 8 || b_st > 36) return fail(FB_ERR_SHAPE, "bad stage counts %d/%d", a_st, b_st);
   const long long smem = (long long)a_st * a_bytes + (long long)b_st * b_bytes + fixed;
-  if (smem > di.smem_optin) return fail(FB_ERR_SHAPE, "shared memory %lld > %d", smem, di.smem_optin);
+  if (smem > smem_cap) return fail(FB_ERR_SHAPE, "shared memory %lld > %d", smem, smem_cap);
   p.a_stages = a_st, p.b_stages = b_st, p.b_resident = b_res;
   p.relu = d->relu, p.store_main = d->store_main, p.acc_init = d->shift_in_acc ? 1 : 0;
   p.scale = d->scale, p.shift = d->shift;
@@ -141,14 +151,14 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   p.mg_nt = magic(p.num_n_tiles), p.mg_tx = magic(p.tiles_x), p.mg_ty = magic(p.tiles_y), p.mg_tb = magic(p.tiles_b);
   if ((double)p.num_m_tiles * p.num_n_tiles * 65536.0 >= 1.0e12) return fail(FB_ERR_SHAPE, "too many tiles");
   p.out_bufs = out_bufs, p.pool_tma = pool_tma, p.prod_tma = prod_tma;
-  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas, pl->ew = ew;
+  pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas, pl->ew = ew, pl->minb = minb;
   return FB_OK;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW>
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1>
 int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY,
                 const CUtensorMap& tP, const CUtensorMap& tQ, cudaStream_t st) {
-  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS, EW>;
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS, EW, MINB>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid), cfg.blockDim = dim3(fb::conv_threads(EW)), cfg.dynamicSmemBytes = pl.smem, cfg.stream = st;
@@ -492,7 +502,7 @@ int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, 
   out->n_tile = pl.n_tile, out->ck = pl.ck, out->halo = pl.halo, out->grid = pl.grid, out->smem_bytes = pl.smem;
   out->ctas = pl.ctas, out->epi_warps = pl.ew, out->a_stages = pl.p.a_stages, out->b_stages = pl.p.b_stages;
   out->b_resident = pl.p.b_resident, out->out_bufs = pl.p.out_bufs, out->total_units = pl.p.total_units;
-  out->pool_tma = pl.p.pool_tma, out->prod_tma = pl.p.prod_tma;
+  out->pool_tma = pl.p.pool_tma, out->prod_tma = pl.p.prod_tma, out->ctas_per_sm = pl.minb;
   return FB_OK;
 }
 
@@ -547,6 +557,10 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
 #define FB_DISPATCH(NT, CK, HL, RS)                                                                     \
   if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) {                            \
     if (pl.ew == 8) FB_LAUNCH(NT, CK, HL, RS, 8)                                                        \
+    if (NT == 64 && HL && RS && pl.minb == 2) {                                                         \
+      if (pl.ctas == 2) return launch_conv<64, CK, true, true, 2, 4, 2>(pl, tA, tB, tY, tP, tQ, st);    \
+      return launch_conv<64, CK, true, true, 1, 4, 2>(pl, tA, tB, tY, tP, tQ, st);                      \
+    }                                                                                                   \
     FB_LAUNCH(NT, CK, HL, RS, 4)                                                                        \
   }
 #define FB_DISPATCH4(NT, CK, HL, RS) \

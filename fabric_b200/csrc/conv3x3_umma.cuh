@@ -149,8 +149,10 @@ __device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int N_TI
   return true;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW>
-__global__ void __launch_bounds__(conv_threads(EW), 1)
+// MINB = 2: two CTAs per SM (64-wide tiles with four epilogue warps only: 192 threads x 168 registers and <= 112 KB of
+// shared memory each) -- two independent tile pipelines per SM hide each other's per-tile latency chain
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1>
+__global__ void __launch_bounds__(conv_threads(EW), MINB)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP,
                     const __grid_constant__ CUtensorMap tmQ, const Conv3x3Params p) {

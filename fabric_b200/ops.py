@@ -126,11 +126,11 @@ def bn_fold_eval(bn: torch.nn.BatchNorm2d, conv_bias: Optional[torch.Tensor]):
     return scale, shift
 
 
-def make_tuning(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, grid=0, ctas=0, epi_warps=0) -> ConvTuning:
-    return ConvTuning(n_tile, halo, a_stages, b_stages, b_resident, grid, ctas, epi_warps)
+def make_tuning(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, grid=0, ctas=0, epi_warps=0, occupancy=0) -> ConvTuning:
+    return ConvTuning(n_tile, halo, a_stages, b_stages, b_resident, grid, ctas, epi_warps, occupancy)
 
 
-DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, grid=0, ctas=0, epi_warps=0)
+DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, grid=0, ctas=0, epi_warps=0, occupancy=0)
 
 
 def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,

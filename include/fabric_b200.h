@@ -69,6 +69,7 @@ typedef struct {
   int grid;        /* 0 = auto (#SMs rounded to a multiple of the N tiles) */
   int ctas;        /* 0 = auto, 1 = one CTA per 128-pixel tile, 2 = CTA pair (tcgen05 cta_group::2, M = 256) */
   int epi_warps;   /* 0 = auto, 4 or 8 epilogue warps (8 only for n_tile <= 128) */
+  int occupancy;   /* 0 / 1 = one CTA per SM; 2 = two (n_tile 64, 4 epilogue warps, halo, resident weights, <= 112 KB smem) */
 } fb_conv_tuning;
 
 typedef struct {
@@ -104,7 +105,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream);
  * per block (B200: 148, 232448).  Pure host arithmetic, no CUDA call: pointers in `d` only need to be NULL / non-NULL. */
 typedef struct {
   int n_tile, ck, halo, grid, smem_bytes, ctas, epi_warps, a_stages, b_stages, b_resident, out_bufs, total_units;
-  int pool_tma, prod_tma;
+  int pool_tma, prod_tma, ctas_per_sm;
 } fb_conv3x3_plan;
 int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, fb_conv3x3_plan* out);
 /* grid the launch above will use, and the stats workspace size (floats) for it */

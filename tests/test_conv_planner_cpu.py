@@ -25,7 +25,8 @@ def plan(lib, G, B, H, W, cin, cout, **kw):
             setattr(d, k, 0x1000)
     d.prod_channels = kw.get("prod_channels", 0)
     d.shift_in_acc = int(kw.get("shift_in_acc", 0))
-    d.tune = _lib.ConvTuning(kw.get("n_tile", 0), -1, 0, 0, -1, 0, kw.get("ctas", 0), kw.get("epi_warps", 0))
+    d.tune = _lib.ConvTuning(kw.get("n_tile", 0), -1, 0, 0, -1, 0, kw.get("ctas", 0), kw.get("epi_warps", 0),
+                             kw.get("occupancy", 0))
     out = _lib.ConvPlan()
     rc = lib.fabric_b200_conv3x3_plan(C.byref(d), SMS, SMEM, C.byref(out))
     return rc, out
@@ -54,9 +55,12 @@ def test_every_layer_has_a_valid_pair_plan(lib, name, G, H, cin, cout, mode):
     rc, p = plan(lib, G, 64, H, H, cin, cout, **kw)
     assert rc == 0, lib.fabric_b200_last_error()
     assert p.smem_bytes <= SMEM
-    assert p.ctas == 2 and p.grid % 2 == 0 and p.grid <= SMS          # CTA pairs on every real layer
+    assert p.ctas == 2 and p.grid % 2 == 0                            # CTA pairs on every real layer
     assert p.n_tile == (64 if cout == 64 else 256 if cout % 256 == 0 else 128)
-    assert p.epi_warps == (8 if p.n_tile <= 128 else 4)
+    stem = cin <= 16
+    assert p.epi_warps == (4 if stem else 8 if p.n_tile <= 128 else 4)
+    assert p.ctas_per_sm == (2 if stem else 1)                         # the stem runs two CTAs per SM
+    assert p.grid <= SMS * p.ctas_per_sm
     assert p.a_stages >= 2 and p.b_stages >= 1
     n_tiles = cout // p.n_tile
     assert (p.grid // 2) % n_tiles == 0                                # each CTA keeps one N tile

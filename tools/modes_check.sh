@@ -1,8 +1,11 @@
-# development checks: parity tests, then single-layer timings (FB_MODE = plain | pool | prod | lean | stats, FB_TUNE = tuning dict)
-timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r01m_bench_infer.json; python - <<EOP
+# development checks: parity tests + both bench workloads
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r01n_bench_infer.json
+timeout 300 python bench.py --steps 15 --warmup 5 --no-cpu-baseline --workload train > gpurun_out/r01n_bench_train.json
+python - <<EOP
 import json
-d=json.loads(open("gpurun_out/r01m_bench_infer.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["roofline"]["achieved"], d["roofline"]["conv_share_of_step"], "e2e", d["e2e"]["value"], "raw", d["e2e_raw_uint16"]["value"])
-for k,v in d["layers"].items(): print(k, round(v["ms"],3), round(v["tflops"]))
+for f in ["r01n_bench_infer.json","r01n_bench_train.json"]:
+    d=json.loads(open("gpurun_out/"+f).read().strip().splitlines()[-1])
+    print(f, round(d["value"]), round(d["ms_per_step"],3), round(d["roofline"]["achieved"]), round(d["roofline"]["conv_share_of_step"],3), "e2e", round(d["e2e"]["value"]), d.get("e2e_raw_uint16") and round(d["e2e_raw_uint16"]["value"]))
+    for k,v in list(d["layers"].items())[:3]: print("  ",k, round(v["ms"],3), round(v["tflops"]))
 EOP

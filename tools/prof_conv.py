@@ -36,6 +36,12 @@ if mode == "stats":
     kw["stats"] = True
 
 
+if os.environ.get("FB_FOLD", "0") == "1":      # eval form: scale folded into the weights, shift preloaded into TMEM
+    wp = ops.pack_conv_weight(w, 0, scale=scale)
+    scale = None
+    kw["shift_in_acc"] = True
+
+
 def run(n):
     for _ in range(n):
         ops.conv3x3(x5, wp, cout, scale, shift, relu=True, tune=tune, out=out, **kw)
