@@ -173,7 +173,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t A_SBO = HALO ? kHaloW * ROW_BYTES : 8 * ROW_BYTES;   // 8-pixel group stride: one (halo) row
   constexpr uint32_t PIX16 = ROW_BYTES >> 4;                              // one pixel in descriptor units
   constexpr uint32_t B_SBO = 8 * ROW_BYTES;
-  constexpr int TMEM_COLS = 2 * N_TILE;
+  // TMEM accumulator ring: four buffers where they fit (64-wide: 256 columns, also twice per SM; 128-wide: all 512), two
+  // for the 256-wide tile.  Tiles of a product pair cost the epilogue very differently (date 1 carries the product), and
+  // with only two buffers the MMA warp stalled on every slow one.
+  constexpr int NACC = N_TILE == 256 ? 2 : 4;
+  constexpr int ACC_SHIFT = NACC == 4 ? 2 : 1;
+  constexpr int TMEM_COLS = NACC * N_TILE;
   constexpr int NCHUNK = N_TILE / 32;
 
   extern __shared__ uint8_t smem_raw[];
@@ -199,7 +204,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto empty_b = [&](int s) { return bars + 8u * (2 * p.a_stages + p.b_stages + s); };
   const uint32_t tf_bar = bars + 8u * (2 * p.a_stages + 2 * p.b_stages);  // tmem_full[2], tmem_empty[2]
   auto tmem_full = [&](int s) { return tf_bar + 8u * s; };
-  auto tmem_empty = [&](int s) { return tf_bar + 16u + 8u * s; };
+  auto tmem_empty = [&](int s) { return tf_bar + 8u * NACC + 8u * s; };
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 1000);
 
   const int warp = threadIdx.x >> 5;
@@ -234,7 +239,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_init(full_b(s), 1);
         mbar_init(empty_b(s), 1);
       }
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < NACC; ++s) {
         mbar_init(tmem_full(s), 1);
         mbar_init(tmem_empty(s), CTAS * (kEpiThreads / 32));
       }
@@ -346,9 +351,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t tile_it = 0;
     TileCoord tc_unused;
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, 0, tc_unused); ++tile_it) {
-      const int acc = tile_it & 1;
+      const int acc = tile_it & (NACC - 1);
       // (acc_init: even the first use of a buffer waits for the epilogue warps, which preload it with the shift)
-      mbar_wait(tmem_empty(acc), ((tile_it >> 1) & 1) ^ (p.acc_init ? 0u : 1u));
+      mbar_wait(tmem_empty(acc), ((tile_it >> ACC_SHIFT) & 1) ^ (p.acc_init ? 0u : 1u));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
       uint32_t accumulate = p.acc_init ? 1u : 0u;
@@ -512,23 +517,22 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       cur_n0 = tc.n0;
       bar_sync(1, kEpiThreads);
-      for (int cc = eg; cc < NCHUNK; cc += kEpiGroups) {
-        preload_shift(0, cc);
-        preload_shift(1, cc);
-      }
+      for (int cc = eg; cc < NCHUNK; cc += kEpiGroups)
+#pragma unroll
+        for (int a_ = 0; a_ < NACC; ++a_) preload_shift(a_, cc);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
 #pragma unroll
-        for (int a_ = 0; a_ < 2; ++a_) {
+        for (int a_ = 0; a_ < NACC; ++a_) {
           if (CTAS == 2) mbar_arrive_cluster(on_leader(tmem_empty(a_)));
           else mbar_arrive(tmem_empty(a_));
         }
       }
     }
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, rank, tc); ++tile_it) {
-      const int acc = tile_it & 1;
+      const int acc = tile_it & (NACC - 1);
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
       const bool valid = gx < pW && gy < pH && gb < pB;
       if (tc.n0 != cur_n0) {
@@ -551,7 +555,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else if (prod_tile) tma_store_wait_all<0>();             // single buffer: date-0 rows are re-read from L2
         else tma_store_wait_read<0>();
       }
-      mbar_wait(tmem_full(acc), (tile_it >> 1) & 1);
+      mbar_wait(tmem_full(acc), (tile_it >> ACC_SHIFT) & 1);
       tc_fence_after();
       __syncwarp();
 
