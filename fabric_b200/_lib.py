@@ -54,6 +54,8 @@ SIGNATURES = {
     "fabric_b200_sm_count": (_i, []),
     "fabric_b200_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_pack_nchw_u16_to_nhwc_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_pack_nchw_aug": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "fabric_b200_augment_labels": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "fabric_b200_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_pack_conv3x3_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_pack_conv3x3_weight_scaled": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -57,8 +57,8 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads):
 
 class _BiDateNetTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, x_d1, x_d2, *params):
-        x5 = model.pack_pair(x_d1, x_d2)
+    def forward(ctx, model, x_d1, x_d2, aug, *params):
+        x5 = model.pack_pair(x_d1, x_d2, aug)
         _, b, h, w, _ = x5.shape
         dev = x5.device
 
@@ -114,9 +114,9 @@ class _BiDateNetTrain(torch.autograd.Function):
         gp1 = _dc_backward(model.down1.mpconv[1], sv["down1"], dcat3, True, gp2, True, grads)
         _dc_backward(model.inc.conv, sv["inc"], dcat4, True, gp1, False, grads)
         ctx.sv = None
-        return (None, None, None) + tuple(grads.get(p) for p in params)
+        return (None, None, None, None) + tuple(grads.get(p) for p in params)
 
 
-def bidatenet_train_forward(model, x_d1, x_d2):
+def bidatenet_train_forward(model, x_d1, x_d2, aug=None):
     params = tuple(model.parameters())
-    return _BiDateNetTrain.apply(model, x_d1.contiguous(), x_d2.contiguous(), *params)
+    return _BiDateNetTrain.apply(model, x_d1.contiguous(), x_d2.contiguous(), aug, *params)

@@ -46,10 +46,20 @@ class BiDateNet(nn.Module):
         self.register_buffer("_fb_in_mean", mean.to(dev).contiguous(), persistent=False)
         self.register_buffer("_fb_in_inv_std", (1.0 / std).to(dev).contiguous(), persistent=False)
 
-    def pack_pair(self, x_d1, x_d2):
-        """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16]."""
+    def pack_pair(self, x_d1, x_d2, aug=None):
+        """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16].  ``aug`` int32 [B,3] (rot90 turns, flip rows, flip columns)
+        applies the loader's augmentation while packing (use ``ops.augment_labels`` with the same rows for the labels)."""
         b, c, h, w = x_d1.shape
         x5 = torch.empty((2, b, h, w, ops.cpad(c)), dtype=torch.bfloat16, device=x_d1.device)
+        if aug is not None:
+            mean, inv_std = getattr(self, "_fb_in_mean", None), getattr(self, "_fb_in_inv_std", None)
+            if x_d1.dtype == torch.uint16 and mean is None:
+                raise RuntimeError("raw uint16 input needs BiDateNet.set_input_normalisation(mean, std) first")
+            if x_d1.dtype != torch.uint16:
+                mean = inv_std = None
+            ops.pack_input_aug(x_d1.contiguous(), aug, mean, inv_std, out=x5[0])
+            ops.pack_input_aug(x_d2.contiguous(), aug, mean, inv_std, out=x5[1])
+            return x5
         if x_d1.dtype == torch.uint16:
             mean, inv_std = getattr(self, "_fb_in_mean", None), getattr(self, "_fb_in_inv_std", None)
             if mean is None:
@@ -101,7 +111,9 @@ class BiDateNet(nn.Module):
         x = self.up4.run5(x, e1["y"])["y"]
         return self.outc.run5(x)
 
-    def forward(self, x_d1, x_d2):
+    def forward(self, x_d1, x_d2, aug=None):
+        """Reference signature ``forward(x_d1, x_d2)`` (models/bidate_model.py:22).  Optional ``aug`` int32 [B,3]: the
+        loader's rot90 / flip augmentation fused into the input pack (see ``pack_pair``)."""
         if x_d1.shape != x_d2.shape:
             raise ValueError("x_d1 and x_d2 must have the same shape")
         if not x_d1.is_cuda:
@@ -109,5 +121,5 @@ class BiDateNet(nn.Module):
                                "call .cuda() on the model and inputs")
         if self.training:
             from .autograd import bidatenet_train_forward
-            return bidatenet_train_forward(self, x_d1, x_d2)
-        return self.forward_packed(self.pack_pair(x_d1, x_d2))
+            return bidatenet_train_forward(self, x_d1, x_d2, aug)
+        return self.forward_packed(self.pack_pair(x_d1, x_d2, aug))

@@ -203,13 +203,32 @@ __global__ void __launch_bounds__(256) pack_nchw_kernel(const float* __restrict_
 // per pixel instead of the smem transpose's ~1000 (that kernel was issue-bound at 23 % of HBM bandwidth).
 // T = float (z-scored patches as the reference's loader hands them over) or unsigned short (raw Sentinel-2 digital numbers:
 // the per-band z-score of utils/dataloaders.py:94-99 is applied here, so the host ships half the bytes).
+// aug (nullable, int32 [B][3] = rot90 quarter turns, flip rows, flip columns; square patches of side S): the loader's
+// augmentation (utils/dataloaders.py:152-163) as a gather -- output pixel (i, j) reads the source pixel that np.rot90 +
+// np.flip would have moved there.
+__device__ __forceinline__ uint32_t aug_source(uint32_t pos, int S, const int* a) {
+  int i = pos / S, j = pos - i * S;
+  const int s1 = S - 1;
+  if (a[2]) j = s1 - j;
+  if (a[1]) i = s1 - i;
+  const int r = a[0] & 3;
+  int si = i, sj = j;
+  if (r == 1) si = j, sj = s1 - i;
+  else if (r == 2) si = s1 - i, sj = s1 - j;
+  else if (r == 3) si = s1 - j, sj = i;
+  return (uint32_t)(si * S + sj);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pack_nchw16_kernel(const T* __restrict__ src, uint32_t* __restrict__ dst, int C,
                                                           uint32_t hw, uint32_t total, const float* __restrict__ mean,
-                                                          const float* __restrict__ inv_std) {
+                                                          const float* __restrict__ inv_std, const int* __restrict__ aug = nullptr,
+                                                          int S = 0) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
   if (i >= total) return;
-  const uint32_t b = i / hw, pos = i - b * hw;
+  const uint32_t b = i / hw;
+  uint32_t pos = i - b * hw;
+  if (aug) pos = aug_source(pos, S, aug + 3 * b);
   const T* s = src + (size_t)b * C * hw + pos;
   float v[16];
 #pragma unroll
@@ -454,6 +473,52 @@ int fabric_b200_pack_nchw_u16_to_nhwc_bf16(const uint16_t* src, void* dst, const
   const uint32_t total = (uint32_t)B * H * W;
   pack_nchw16_kernel<unsigned short><<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       src, reinterpret_cast<uint32_t*>(dst), C, (uint32_t)H * W, total, mean, inv_std);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+__global__ void augment_labels_kernel(const long long* __restrict__ src, long long* __restrict__ dst, const int* __restrict__ aug,
+                                      int S, uint32_t total) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const uint32_t hw = (uint32_t)S * S, b = i / hw;
+  dst[i] = src[(size_t)b * hw + aug_source(i - b * hw, S, aug + 3 * b)];
+}
+
+int fabric_b200_pack_nchw_aug(const void* src, int src_dtype, void* dst, const int* aug, const float* mean,
+                              const float* inv_std, int B, int C, int S, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!src || !dst || !aug) return fail(FB_ERR_ARG, "null pointer");
+  if ((mean == nullptr) != (inv_std == nullptr)) return fail(FB_ERR_ARG, "mean and inv_std go together");
+  if (C < 1 || C > 16 || B < 1 || S < 1 || (double)B * S * S >= 4.0e9) return fail(FB_ERR_SHAPE, "bad shape");
+  if ((uintptr_t)dst & 31) return fail(FB_ERR_ALIGN, "dst must be 32-byte aligned");
+  const uint32_t total = (uint32_t)B * S * S;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == 0)
+    pack_nchw16_kernel<float><<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(src),
+                                                                  reinterpret_cast<uint32_t*>(dst), C, (uint32_t)S * S, total,
+                                                                  mean, inv_std, aug, S);
+  else if (src_dtype == 1)
+    pack_nchw16_kernel<unsigned short><<<(total + 255) / 256, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(src),
+                                                                           reinterpret_cast<uint32_t*>(dst), C, (uint32_t)S * S,
+                                                                           total, mean, inv_std, aug, S);
+  else
+    return fail(FB_ERR_ARG, "src_dtype must be 0 (fp32) or 1 (uint16)");
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_augment_labels(const int64_t* src, int64_t* dst, const int* aug, int B, int S, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!src || !dst || !aug || src == dst) return fail(FB_ERR_ARG, "null pointer or in-place call");
+  if (B < 1 || S < 1 || (double)B * S * S >= 4.0e9) return fail(FB_ERR_SHAPE, "bad shape");
+  const uint32_t total = (uint32_t)B * S * S;
+  augment_labels_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(src), reinterpret_cast<long long*>(dst), aug, S, total);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

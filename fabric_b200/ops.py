@@ -82,6 +82,32 @@ def pack_input_raw(x: torch.Tensor, mean: torch.Tensor, inv_std: torch.Tensor, o
     return out
 
 
+def pack_input_aug(x: torch.Tensor, aug: torch.Tensor, mean=None, inv_std=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW [B,C,S,S] fp32 or uint16 -> NHWC bf16 [B,S,S,16] of the AUGMENTED patch; ``aug`` int32 [B,3] = (rot90 quarter
+    turns, flip rows, flip columns) per sample (reference utils/dataloaders.py:152-163)."""
+    _need_cuda(x, aug, mean, inv_std, out)
+    b, c, s, s2 = x.shape
+    assert s == s2 and aug.dtype == torch.int32 and aug.shape == (b, 3)
+    dt = {torch.float32: 0, torch.uint16: 1}[x.dtype]
+    if out is None:
+        out = torch.empty((b, s, s, 16), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().fabric_b200_pack_nchw_aug(_p(x), dt, _p(out), _p(aug), _p(mean), _p(inv_std), b, c, s, _stream()),
+          "pack_input_aug")
+    _count()
+    return out
+
+
+def augment_labels(labels: torch.Tensor, aug: torch.Tensor) -> torch.Tensor:
+    """labels int64 [B,S,S] -> the same rot90 / flips as ``pack_input_aug`` (out of place)."""
+    _need_cuda(labels, aug)
+    b, s, s2 = labels.shape
+    assert s == s2 and labels.dtype == torch.int64 and aug.dtype == torch.int32 and aug.shape == (b, 3)
+    out = torch.empty_like(labels)
+    check(_lib.load().fabric_b200_augment_labels(_p(labels), _p(out), _p(aug), b, s, _stream()), "augment_labels")
+    _count()
+    return out
+
+
 def unpack_output(x: torch.Tensor) -> torch.Tensor:
     """NHWC bf16 [B,H,W,C] -> NCHW fp32 [B,C,H,W]."""
     _need_cuda(x)

@@ -46,6 +46,13 @@ int fabric_b200_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int B, i
  * over the rasters as stored (half the bytes of the reference's fp32 patches at train.py:189-190). */
 int fabric_b200_pack_nchw_u16_to_nhwc_bf16(const uint16_t* src, void* dst, const float* mean, const float* inv_std, int B,
                                            int C, int H, int W, void* stream);
+/* Training patches with the loader's augmentation fused (onera_siamese_loader, utils/dataloaders.py:152-163): src NCHW
+ * [B][C][S][S] (src_dtype 0 = fp32, 1 = uint16 with mean / inv_std as above, both nullable for fp32), aug int32 [B][3] =
+ * (rot90 quarter turns, flip rows, flip columns) per sample -> NHWC bf16 [B][S][S][16] of the augmented patch.  The same
+ * `aug` rows are applied to the labels int64 [B][S][S] by fabric_b200_augment_labels (out of place). */
+int fabric_b200_pack_nchw_aug(const void* src, int src_dtype, void* dst, const int* aug, const float* mean,
+                              const float* inv_std, int B, int C, int S, void* stream);
+int fabric_b200_augment_labels(const int64_t* src, int64_t* dst, const int* aug, int B, int S, void* stream);
 /* NHWC bf16 [B][H][W][C] -> NCHW fp32 [B][C][H][W] (standalone block outputs / tests). */
 int fabric_b200_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int B, int C, int H, int W, void* stream);
 

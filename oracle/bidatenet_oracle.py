@@ -356,3 +356,36 @@ def get_bands(patches: np.ndarray, hs, ws, lc, lr, h, w, patch_size: int = 64) -
         img[h - patch_size:, i * patch_size:(i + 1) * patch_size] = last_row[i]
     img[h - patch_size:, w - patch_size:] = corner
     return img
+
+
+# ------------------------------------------------------------------------------------------------ augmentation
+def augment_patch(img: np.ndarray, lbl: np.ndarray, rot_deg: int, flip0: bool, flip1: bool):
+    """Reference utils/dataloaders.py:152-163 (`onera_siamese_loader`, aug branch) with the three random draws made
+    explicit: ``img`` [2, C, S, S] (both dates), ``lbl`` [S, S]; rot90 by ``rot_deg`` quarter turns, then the two flips."""
+    out_img = np.rot90(img, rot_deg, [2, 3]).copy()              # :153
+    out_lbl = np.rot90(lbl, rot_deg, [0, 1]).copy()              # :154
+    if flip0:                                                    # :156-158
+        out_img = np.flip(out_img, axis=2).copy()
+        out_lbl = np.flip(out_lbl, axis=0).copy()
+    if flip1:                                                    # :160-162
+        out_img = np.flip(out_img, axis=3).copy()
+        out_lbl = np.flip(out_lbl, axis=1).copy()
+    return out_img, out_lbl
+
+
+def augment_source_index(i: int, j: int, size: int, rot_deg: int, flip0: bool, flip1: bool):
+    """(row, col) in the UN-augmented patch that lands at (i, j) after `augment_patch` -- the gather form the device
+    kernel uses (fabric_b200/csrc/capi.cu: pack_nchw16_kernel with `aug`)."""
+    s1 = size - 1
+    if flip1:
+        j = s1 - j
+    if flip0:
+        i = s1 - i
+    rot_deg %= 4
+    if rot_deg == 1:
+        return j, s1 - i
+    if rot_deg == 2:
+        return s1 - i, s1 - j
+    if rot_deg == 3:
+        return s1 - j, i
+    return i, j

@@ -447,3 +447,40 @@ def test_raw_uint16_input_matches_oracle_on_normalised_input(cuda):
     h2d, _ = pipe.run(raw[0].pin_memory(), raw[1].pin_memory(), host_out)
     torch.cuda.synchronize()
     assert h2d == 2 * raw[0].numel() * 2 and torch.equal(host_out, out)
+
+
+def test_fused_augmentation_matches_reference_loader(cuda):
+    """rot90 / flips fused into the input pack (and applied to the labels) == the reference loader's numpy ops
+    (utils/dataloaders.py:152-163) followed by the plain pack, bit-exact, fp32 and raw uint16 inputs."""
+    import numpy as np
+    from fabric_b200 import ops
+    from oracle import bidatenet_oracle as O
+    rng = np.random.default_rng(9)
+    B, C, S = 8, 13, 24
+    img = rng.standard_normal((B, 2, C, S, S)).astype(np.float32)
+    lbl = rng.integers(0, 2, (B, S, S)).astype(np.int64)
+    params = [(b % 4, (b // 2) % 2, (b // 4) % 2) for b in range(B)] 
+    aug = torch.tensor(params, dtype=torch.int32, device=cuda)
+    want_img = np.stack([O.augment_patch(img[b], lbl[b], *params[b])[0] for b in range(B)])
+    want_lbl = np.stack([O.augment_patch(img[b], lbl[b], *params[b])[1] for b in range(B)])
+    for d in range(2):
+        got = ops.pack_input_aug(torch.from_numpy(img[:, d].copy()).to(cuda), aug)
+        ref = ops.pack_input(torch.from_numpy(want_img[:, d].copy()).to(cuda))
+        assert torch.equal(got, ref)
+    assert torch.equal(ops.augment_labels(torch.from_numpy(lbl).to(cuda), aug).cpu(), torch.from_numpy(want_lbl.copy()))
+    # raw uint16 + z-score + augmentation in one pass
+    raw = rng.integers(0, 4000, (B, C, S, S)).astype(np.uint16)
+    mean = torch.linspace(500, 2500, C, device=cuda)
+    inv_std = 1.0 / torch.linspace(200, 900, C, device=cuda)
+    want_raw = np.stack([O.augment_patch(np.stack([raw[b], raw[b]]), lbl[b], *params[b])[0][0] for b in range(B)])
+    got = ops.pack_input_aug(torch.from_numpy(raw).to(cuda), aug, mean, inv_std)
+    ref = ops.pack_input_raw(torch.from_numpy(want_raw.copy()).to(cuda), mean, inv_std)
+    assert torch.equal(got, ref)
+    # through the model entry point
+    sd = O.make_state_dict(seed=0)
+    model = _model(cuda, sd)
+    x1, x2 = torch.from_numpy(img[:, 0].copy()).to(cuda), torch.from_numpy(img[:, 1].copy()).to(cuda)
+    with torch.no_grad():
+        a = model(x1, x2, aug=aug)
+        b_ = model(torch.from_numpy(want_img[:, 0].copy()).to(cuda), torch.from_numpy(want_img[:, 1].copy()).to(cuda))
+    assert torch.equal(a, b_)

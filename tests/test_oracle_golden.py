@@ -116,3 +116,23 @@ def test_tile_origins_match_oracle_tiler():
         assert (hs, ws, lc, lr) == (hs2, ws2, lc2, lr2) and len(org) == patches.shape[0]
         for k, (y, x) in enumerate(org):
             assert patches[k, 0, 0, 0] == y * w + x
+
+
+def test_augmentation_gather_form_matches_numpy_rot_flip():
+    """The index map the device kernel uses == np.rot90 + np.flip exactly as the reference loader applies them
+    (utils/dataloaders.py:152-163), for every (rot, flip, flip) combination."""
+    import numpy as np
+    from oracle import bidatenet_oracle as O
+    rng = np.random.default_rng(3)
+    S = 7
+    img = rng.standard_normal((2, 3, S, S)).astype(np.float32)
+    lbl = rng.integers(0, 2, (S, S)).astype(np.uint8)
+    for rot in range(4):
+        for f0 in (False, True):
+            for f1 in (False, True):
+                a_img, a_lbl = O.augment_patch(img, lbl, rot, f0, f1)
+                for i in range(S):
+                    for j in range(S):
+                        si, sj = O.augment_source_index(i, j, S, rot, f0, f1)
+                        assert a_lbl[i, j] == lbl[si, sj]
+                        assert np.array_equal(a_img[:, :, i, j], img[:, :, si, sj])
