@@ -245,6 +245,7 @@ def main():
     ap.add_argument("--impl", default="fabric_b200", choices=["fabric_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunk", type=int, default=32, help="pairs per sub-batch of the host pipeline (e2e leg)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -392,14 +393,14 @@ def main():
                "SGD.step(); loss.item()")
     else:
         hout = torch.empty(PAIRS, 2, SIZE, SIZE).pin_memory()
-        pipe = HostPipeline(model, chunk=16, n_channels=13, size=SIZE, return_logits=True)
+        pipe = HostPipeline(model, chunk=args.e2e_chunk, n_channels=13, size=SIZE, return_logits=True)
         res = {}
 
         def e2e_step():
             res["b"] = pipe.run(hp1, hp2, hout)
         e2e_step()
         h2d, d2h = res["b"]
-        api = "fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, 16-pair sub-batches)"
+        api = f"fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, {args.e2e_chunk}-pair sub-batches)"
     def timed_e2e(fn):
         for _ in range(2):
             fn()
