@@ -8,7 +8,7 @@ namespace {
 
 struct WgPlan {
   fb::WgradParams p;
-  int qck, grid, smem, wide;
+  int qck, grid, smem, wide, v2;
 };
 
 int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
@@ -32,9 +32,17 @@ int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
   p.tiles_b = (d->B + p.bn - 1) / p.bn;
   p.tiles_total = p.tiles_x * p.tiles_y * p.tiles_b * d->G;
   pl->qck = d->Cb == 16 ? 16 : 64;
+  // second form (filter row through the Q halo tile, 32-channel Q chunks): every layer but the 13-band stem and the
+  // tiny maps of the tests; wide = 0 / 1 select the first form explicitly
+  // Measured (64 pairs, both forms on every layer, tools/prof_wgrad.py): the second form trades L2 reads for A-operand
+  // shared-memory reads (each P slice is read once per filter row) and wins where the first one is L2-bound hardest --
+  // 64->128 0.385 -> 0.324 ms, 128->128 0.627 -> 0.520 ms, 128->256 0.303 -> 0.260 ms -- and loses on Ca = 64 (half of
+  // M is padding) and on wide Q (Cb >= 256).  wide = 3 picks per shape.
+  const bool v2_ok = d->Cb % 64 == 0 && p.bh == 16;
+  pl->v2 = (v2_ok && (d->wide == 2 || (d->wide == 3 && d->Ca >= 128 && d->Cb <= 128))) ? 1 : 0;
   p.m_tiles = (d->Ca + 127) / 128;
-  p.n_chunks = d->Cb / pl->qck;
-  p.row_items = d->Ca == 64 ? 2 : 3;
+  p.n_chunks = pl->v2 ? d->Cb / 32 : d->Cb / pl->qck;
+  p.row_items = pl->v2 ? 1 : (d->Ca == 64 ? 2 : 3);
   const int items = p.m_tiles * p.n_chunks * p.row_items;
   int splits = d->splits;
   if (splits <= 0) {
@@ -44,7 +52,7 @@ int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
     if (splits < 1) splits = 1;
   }
   p.splits = splits;
-  const int stage = fb::wg_stage_bytes(pl->qck);
+  const int stage = pl->v2 ? fb::kWg2Stage : fb::wg_stage_bytes(pl->qck);
   int stages = (di.smem_optin - 2048) / stage;
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(FB_ERR_SHAPE, "not enough shared memory");
@@ -91,10 +99,18 @@ int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream) {
   CUtensorMap tP, tQ;
   rc = make_tmap_act(&tP, d->p, p.Ca, p.W, p.H, p.B, p.G, 64, 8, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, pl.qck, 10, p.bh, p.bn,
-                     pl.qck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (pl.v2) rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, 32, 10, 18, 1, CU_TENSOR_MAP_SWIZZLE_64B);
+  else rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, pl.qck, 10, p.bh, p.bn,
+                          pl.qck == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl.v2) {
+    auto k = fb::wgrad2_umma_kernel;
+    FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+    k<<<pl.grid, fb::kWgThreads, pl.smem, st>>>(tP, tQ, pl.p);
+    FB_CUDA(cudaGetLastError());
+    return FB_OK;
+  }
   if (pl.qck == 64) return pl.wide ? launch_wgrad<64, true>(pl, tP, tQ, st) : launch_wgrad<64, false>(pl, tP, tQ, st);
   return pl.wide ? launch_wgrad<16, true>(pl, tP, tQ, st) : launch_wgrad<16, false>(pl, tP, tQ, st);
 }

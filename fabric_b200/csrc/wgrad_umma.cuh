@@ -201,4 +201,150 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second form (used for Cb % 64 == 0 on maps of 16 rows or more): the filter ROW is applied through the Q tile as well.
+// Work item = (128 P channels, 32 Q channels, K split); per pixel tile ONE P tile (rows y0..y0+15) and ONE Q tile with its
+// full halo (18 rows x 10 columns x 32 channels, 64B swizzle) feed all nine taps: for each 16-pixel K slice j and filter row
+// r one N = 96 MMA (three 32-channel N atoms = the same buffer at leading-byte-offset one pixel, start address at halo row
+// 2j + r) into accumulator r.  The first form re-reads 52 KB from L2 per (filter row, 64 Q channels) item -- 121 flop per L2
+// byte, L2-bound at ~10 TB/s -- this one moves 43.5 KB per 32 Q channels for all three rows: 217 flop per byte.
+constexpr int kWg2PBytes = 2 * 16384;
+constexpr int kWg2QBytes = 12288;                       // 18 x 10 pixels x 64 B = 11520, rounded up to 1 KB
+constexpr int kWg2Stage = kWg2PBytes + kWg2QBytes;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad2_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_u32);
+  const uint32_t bar_off = p.stages * kWg2Stage;
+  const uint32_t bars = base + bar_off;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (p.stages + s); };
+  const uint32_t done_bar = bars + 8u * (2 * p.stages);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int it = blockIdx.x;
+  const int split = it % p.splits;
+  it /= p.splits;
+  const int nc = it % p.n_chunks;       // 32-channel Q chunk
+  const int mt = it / p.n_chunks;       // 128-channel P tile
+  const int ca_a = mt * 128;
+  const int ca_b = ca_a + 64 < p.Ca ? ca_a + 64 : p.Ca;   // beyond Ca: the box is out of bounds = zero filled
+  const int t_begin = (int)((long long)p.tiles_total * split / p.splits);
+  const int t_end = (int)((long long)p.tiles_total * (split + 1) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP);
+    prefetch_tmap(&tmQ);
+  }
+  if (warp == 1) {
+    tmem_alloc(base + bar_off + 512, 512);
+    tmem_relinquish();
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full(s), 1);
+        mbar_init(empty(s), 1);
+      }
+      mbar_init(done_bar, 1);
+      fence_mbar_init();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      int m = t;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      m /= p.tiles_y;
+      const int tb = m % p.tiles_b;
+      const int g = m / p.tiles_b;
+      const int x0 = tx * 8, y0 = ty * 16, b0 = tb;
+      mbar_wait(empty(stage), phase ^ 1);
+      if (elect_one()) {
+        const uint32_t dst = base + stage * kWg2Stage;
+        mbar_arrive_expect_tx(full(stage), kWg2PBytes + 18 * 10 * 64);
+        tma_load_5d(dst, &tmP, full(stage), ca_a, x0, y0, b0, g);
+        tma_load_5d(dst + 16384, &tmP, full(stage), ca_b, x0, y0, b0, g);
+        tma_load_5d(dst + kWg2PBytes, &tmQ, full(stage), nc * 32, x0 - 1, y0 - 1, b0, g);
+      }
+      __syncwarp();
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else if (warp == 1) {
+    // A: M = P channels (MN-major, 128B swizzle), 2 atoms of 64 at LBO = 16384, K groups of 8 pixels at SBO = 1024
+    // B: N = 3 x 32 Q channels (MN-major, 64B swizzle), N atoms at LBO = 64 B (one pixel), K groups at SBO = 640 B (halo row)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 96, 1, 1);
+    constexpr uint64_t a_hi = umma_desc(0, 16384, 1024, kLayoutSw128) & 0xFFFFFFFF00000000ull;
+    constexpr uint64_t b_hi = umma_desc(0, 64, 640, kLayoutSw64) & 0xFFFFFFFF00000000ull;
+    constexpr uint32_t a_lo_fixed = static_cast<uint32_t>(umma_desc(0, 16384, 0, 0) & 0xFFFFFFFFu);
+    constexpr uint32_t b_lo_fixed = static_cast<uint32_t>(umma_desc(0, 64, 0, 0) & 0xFFFFFFFFu);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(full(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo_fixed + ((base + stage * kWg2Stage) >> 4);
+        const uint32_t b_lo = b_lo_fixed + ((base + stage * kWg2Stage + kWg2PBytes) >> 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {       // 16 pixels (two tile rows) per K slice
+#pragma unroll
+          for (int r = 0; r < 3; ++r)       // filter row: the Q window starts r halo rows further down
+            umma_bf16(tmem_base + r * 96, a_hi | (a_lo + j * 128), b_hi | (b_lo + (2 * j + r) * 40), idesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(empty(stage));
+        if (t == t_end - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else {
+    // epilogue: 128 rows (P channels) x 9 taps x 32 Q channels -> fp32 partial slab of this split
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ca = ca_a + row;
+    if (t_end > t_begin) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      uint32_t v[32];
+      if (t_end > t_begin) {
+        tmem_ld_32x32(tmem_base + (tap / 3) * 96 + (tap % 3) * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (ca < p.Ca) {
+        float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)split * p.Ca + ca) * 9 + tap) * p.Cb + nc * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace fb

@@ -254,7 +254,9 @@ def outconv(x5: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
 
 
 # ------------------------------------------------------------------------------------------------ training ops
-WGRAD_WIDE = 1   # one N=3*64 MMA per K step (overlapping N atoms one pixel apart); validated bit-level against the 3-MMA form
+# 1: one N=3*64 MMA per K step (overlapping N atoms one pixel apart; validated bit-level against the 3-MMA form 0);
+# 2: filter row through an 18-row Q halo tile; 3: per-shape choice between 1 and 2 (see fabric_b200/csrc/wgrad.cu)
+WGRAD_WIDE = 3
 
 
 def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_per_group: int, groups: int):

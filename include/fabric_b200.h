@@ -200,7 +200,10 @@ typedef struct {
   const void* q;   /* bf16 [G][B][H][W][Cb] */
   float* ws;       /* fp32 [splits][Ca][9][Cb], fabric_b200_conv3x3_wgrad_ws_floats() */
   int splits;      /* 0 = auto */
-  int wide;        /* 1 = one N=3*Cb-chunk MMA per K step (overlapping N atoms), 0 = three MMAs */
+  int wide;        /* 0 = three N=64 MMAs per K step, 1 = one N=192 MMA (overlapping N atoms), 2 = second form: the filter
+                      row goes through an 18-row Q halo tile, 32-channel Q chunks, three N=96 MMAs per K step (falls back
+                      to 1 for Cb = 16 and maps of 8 rows or fewer), 3 = 2 where it measured faster (Ca >= 128 and
+                      Cb <= 128), else 1 */
 } fb_wgrad_desc;
 int64_t fabric_b200_conv3x3_wgrad_ws_floats(const fb_wgrad_desc* d);
 int fabric_b200_conv3x3_wgrad_splits(const fb_wgrad_desc* d);
