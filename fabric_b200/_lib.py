@@ -46,6 +46,10 @@ class WgradDesc(C.Structure):
                 ("p", C.c_void_p), ("q", C.c_void_p), ("ws", C.c_void_p), ("splits", C.c_int), ("wide", C.c_int)]
 
 
+class WgradPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("form", "grid", "items", "splits", "stages", "smem_bytes", "tiles_total")]
+
+
 # name -> (restype, argtypes); every symbol declared in include/fabric_b200.h
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 SIGNATURES = {
@@ -76,6 +80,7 @@ SIGNATURES = {
     "fabric_b200_bn_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_up_input_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_conv3x3_wgrad_plan": (_i, [C.POINTER(WgradDesc), _i, _i, C.POINTER(WgradPlan)]),
     "fabric_b200_conv3x3_wgrad_ws_floats": (_i64, [C.POINTER(WgradDesc)]),
     "fabric_b200_conv3x3_wgrad_splits": (_i, [C.POINTER(WgradDesc)]),
     "fabric_b200_conv3x3_wgrad": (_i, [C.POINTER(WgradDesc), _vp]),

@@ -11,11 +11,19 @@ struct WgPlan {
   int qck, grid, smem, wide, v2;
 };
 
+int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di);
+
 int plan_wgrad(const fb_wgrad_desc* d, WgPlan* pl) {
   if (!d) return fail(FB_ERR_ARG, "null descriptor");
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
+  return plan_wgrad_on(d, pl, di);
+}
+
+// the launch plan as a pure function of the descriptor and the device limits (no CUDA calls: testable without a GPU)
+int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di) {
+  if (!d) return fail(FB_ERR_ARG, "null descriptor");
   if (d->G < 1 || d->G > 2 || d->B < 1 || d->H < 1 || d->W < 1) return fail(FB_ERR_SHAPE, "bad G/B/H/W");
   if (d->Ca <= 0 || d->Ca % 64) return fail(FB_ERR_SHAPE, "Ca %d must be a multiple of 64", d->Ca);
   if (!(d->Cb == 16 || (d->Cb > 0 && d->Cb % 64 == 0))) return fail(FB_ERR_SHAPE, "Cb %d must be 16 or k*64", d->Cb);
@@ -86,6 +94,18 @@ int launch_wgrad(const WgPlan& pl, const CUtensorMap& tP, const CUtensorMap& tQ,
 }  // namespace
 
 extern "C" {
+
+int fabric_b200_conv3x3_wgrad_plan(const fb_wgrad_desc* d, int sms, int smem_optin, fb_wgrad_plan* out) {
+  if (!d || !out) return fail(FB_ERR_ARG, "null pointer");
+  DeviceInfo di;
+  di.ok = 1, di.sms = sms, di.smem_optin = smem_optin;
+  WgPlan pl;
+  int rc = plan_wgrad_on(d, &pl, di);
+  if (rc) return rc;
+  out->form = pl.v2 ? 2 : 1, out->grid = pl.grid, out->splits = pl.p.splits, out->stages = pl.p.stages;
+  out->smem_bytes = pl.smem, out->items = pl.grid / pl.p.splits, out->tiles_total = pl.p.tiles_total;
+  return FB_OK;
+}
 
 int64_t fabric_b200_conv3x3_wgrad_ws_floats(const fb_wgrad_desc* d) {
   WgPlan pl;

@@ -205,6 +205,12 @@ typedef struct {
                       to 1 for Cb = 16 and maps of 8 rows or fewer), 3 = 2 where it measured faster (Ca >= 128 and
                       Cb <= 128), else 1 */
 } fb_wgrad_desc;
+/* the launch plan on a device with `sms` SMs / `smem_optin` bytes of opt-in shared memory (pure host arithmetic) */
+typedef struct {
+  int form;        /* 1 = filter row through the P tile, 2 = through the Q halo tile */
+  int grid, items, splits, stages, smem_bytes, tiles_total;
+} fb_wgrad_plan;
+int fabric_b200_conv3x3_wgrad_plan(const fb_wgrad_desc* d, int sms, int smem_optin, fb_wgrad_plan* out);
 int64_t fabric_b200_conv3x3_wgrad_ws_floats(const fb_wgrad_desc* d);
 int fabric_b200_conv3x3_wgrad_splits(const fb_wgrad_desc* d);
 int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream);

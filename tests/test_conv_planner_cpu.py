@@ -110,3 +110,39 @@ def test_bad_requests_are_refused(lib):
     assert plan(lib, 1, 1, 16, 8, 64, 64, ctas=2)[0] != 0               # a single pixel tile cannot form a pair
     assert plan(lib, 1, 2, 16, 16, 64, 256, epi_warps=8)[0] != 0        # 8 epilogue warps only up to 128-wide tiles
     assert plan(lib, 1, 2, 16, 16, 64, 64, shift_in_acc=1)[0] != 0      # needs the shift vector
+
+
+# ---------------------------------------------------------------------------------------------- weight gradient
+def wgrad_plan(lib, G, B, H, W, ca, cb, wide=3, splits=0):
+    from fabric_b200 import _lib
+    d = _lib.WgradDesc()
+    d.G, d.B, d.H, d.W, d.Ca, d.Cb = G, B, H, W, ca, (16 if cb <= 16 else cb)
+    d.p = d.q = d.ws = 0x1000
+    d.splits, d.wide = splits, wide
+    out = _lib.WgradPlan()
+    rc = lib.fabric_b200_conv3x3_wgrad_plan(C.byref(d), SMS, SMEM, C.byref(out))
+    return rc, out
+
+
+@pytest.mark.parametrize("name,G,H,cin,cout", LAYERS)
+def test_wgrad_grid_fills_whole_waves(lib, name, G, H, cin, cout):
+    """The weight-gradient grid is not persistent: the planner must not leave a mostly empty last wave (profiles/
+    r01_ncu_full_wgrad.md), and it picks the second form exactly where it measured faster."""
+    rc, p = wgrad_plan(lib, G, 64, H, H, cout, cin)          # P = dL/dz has the layer's OUTPUT channels
+    assert rc == 0, lib.fabric_b200_last_error()
+    assert p.smem_bytes <= SMEM and p.stages >= 2
+    assert p.form == (2 if (cout >= 128 and 64 <= cin <= 128) else 1)
+    assert p.grid == p.items * p.splits and p.splits * 4 <= p.tiles_total
+    waves = -(-p.grid // SMS)
+    assert p.grid / (waves * SMS) >= 0.85, (p.grid, waves)    # every wave at least 85 % full
+    # no other split count (within the planner's search range) does better by more than rounding
+    best = min(-(-p.items * s // SMS) / s for s in range(1, min(4 * SMS // p.items + 1, p.tiles_total // 4) + 1))
+    assert waves / p.splits <= best * 1.001
+
+
+def test_wgrad_forms_and_fallbacks(lib):
+    assert wgrad_plan(lib, 2, 64, 128, 128, 128, 128, wide=1)[1].form == 1
+    assert wgrad_plan(lib, 2, 64, 128, 128, 128, 128, wide=2)[1].form == 2
+    assert wgrad_plan(lib, 2, 64, 256, 256, 64, 13, wide=2)[1].form == 1      # 13-band stem: first form only
+    assert wgrad_plan(lib, 2, 5, 4, 4, 128, 128, wide=2)[1].form == 1         # maps of 8 rows or fewer
+    assert wgrad_plan(lib, 1, 1, 16, 16, 96, 64)[0] != 0                      # Ca must be a multiple of 64
