@@ -25,3 +25,18 @@ def built_lib():
     g.build()
     from fabric_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _gpu_quiesce(request):
+    """GPU tests start and end with an idle device: no test inherits another test's in-flight work (side-stream copies,
+    deferred frees), so a failure always belongs to the test that reports it."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    yield
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()

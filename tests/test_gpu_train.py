@@ -51,8 +51,12 @@ def test_losses_match_oracle(cuda, kind, nd):
     l = logits.clone().requires_grad_(True)
     v = fn(l, lab)
     v.backward()
-    loss, dl = ops.seg_loss_fwd_bwd(kind, logits.to(cuda), lab.to(cuda), 0.1, 0.9, 2.0, 1e-7)
-    assert abs(float(loss) - float(v.detach())) <= 2e-6
+    dev_logits, dev_lab = logits.to(cuda), lab.to(cuda)
+    loss, dl = ops.seg_loss_fwd_bwd(kind, dev_logits, dev_lab, 0.1, 0.9, 2.0, 1e-7)
+    loss2, dl2 = ops.seg_loss_fwd_bwd(kind, dev_logits, dev_lab, 0.1, 0.9, 2.0, 1e-7)
+    got, got2, want = float(loss), float(loss2), float(v.detach())
+    assert got == got2 and torch.equal(dl, dl2), f"fused {kind} loss is not deterministic: {got!r} vs {got2!r}"
+    assert abs(got - want) <= 2e-6, f"{kind}: fused {got!r} vs oracle {want!r}"
     assert rel(dl.cpu(), l.grad) <= 1e-4
 
 
