@@ -89,6 +89,7 @@ SIGNATURES = {
     "fabric_b200_argmax_metrics": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "fabric_b200_scatter_tiles": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_sgd_step": (_i, [_vp, _i, _f, _f, _vp]),
+    "fabric_b200_train_step_update": (_i, [_vp, _i, _f, _f, _f, _vp]),
 }
 
 _lib = None

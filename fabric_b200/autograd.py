@@ -6,6 +6,10 @@ bn_finalize (batch statistics per date group, running-stat update) -> bn_apply (
 Backward: outconv_bwd -> per block [bn_relu_bwd (with the product-fusion / max-pool adjoints fused into its reads) ->
 wgrad (tcgen05) + dgrad (the forward conv kernel with tap-flipped weights)] -> up_input_bwd between decoder stages.
 Everything stays NHWC bf16 on the device; gradients of the fp32 parameters come back in nn.Conv2d / BatchNorm layout.
+
+Gradient sink: when a ``fabric_b200.distributed.DataParallelStep`` owns the model, every parameter gradient is written
+by the producing kernel STRAIGHT into that step's flat all-reduce bucket (``p.grad`` is a view of it) and the Function
+returns ``None`` for the parameters -- no gradient tensor is allocated, copied or accumulated by torch.
 """
 from __future__ import annotations
 
@@ -16,6 +20,9 @@ from . import ops
 KEEP_SAVED = False   # tests: keep the stored forward tensors of the last training forward in LAST_SAVED
 LAST_SAVED = None
 
+# backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
+BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")
+
 
 def _dc_forward(dc, x5, pool, prod_out=None):
     """double_conv in training mode.  Returns (a2, pooled, saved).  ``prod_out``: decoder input whose skip half
@@ -23,36 +30,39 @@ def _dc_forward(dc, x5, pool, prod_out=None):
     c1, b1, c2, b2 = dc.conv[0], dc.conv[1], dc.conv[3], dc.conv[4]
     g, b, h, w, _ = x5.shape
     n = b * h * w
-    r1 = ops.conv3x3(x5, dc._packed(0), dc.out_ch, stats=True, tune=dc.tune1, true_cin=dc.in_ch)
+    r1 = ops.conv3x3(x5, dc._packed(0, training=True), dc.out_ch, stats=True, tune=dc.tune1, true_cin=dc.in_ch)
     s1 = ops.bn_finalize(r1["stats"], b1, c1.bias, n, g)
     a1, _ = ops.bn_apply_relu(r1["y"], s1[0], s1[1])
-    r2 = ops.conv3x3(a1, dc._packed(3), dc.out_ch, stats=True, tune=dc.tune2)
+    r2 = ops.conv3x3(a1, dc._packed(3, training=True), dc.out_ch, stats=True, tune=dc.tune2)
     s2 = ops.bn_finalize(r2["stats"], b2, c2.bias, n, g)
     a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out)
     saved = dict(x=x5, z1=r1["y"], a1=a1, z2=r2["y"], a2=a2, s1=s1, s2=s2)
     return a2, pooled, saved
 
 
-def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads):
-    """Backward of one double_conv.  ga / gp: gradient sources for its output activation (see ops.bn_relu_bwd)."""
+def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None):
+    """Backward of one double_conv.  ga / gp: gradient sources for its output activation (see ops.bn_relu_bwd).
+    ``sink``: {parameter: gradient tensor to write into} (the data-parallel bucket views) or None."""
     c1, b1, c2, b2 = dc.conv[0], dc.conv[1], dc.conv[3], dc.conv[4]
+    sink = sink or {}
     need_a = mul_other or gp is not None
-    dz2, dg2, db2 = ops.bn_relu_bwd(sv["z2"], sv["a2"] if need_a else None, ga, mul_other, gp, *sv["s2"], b2.weight)
-    grads[c2.weight] = ops.conv3x3_wgrad(dz2, sv["a1"], dc.out_ch)
-    grads[c2.bias] = torch.zeros_like(c2.bias)          # a conv bias in front of a train-mode BN has zero gradient
+    dz2, dg2, db2 = ops.bn_relu_bwd(sv["z2"], sv["a2"] if need_a else None, ga, mul_other, gp, *sv["s2"], b2.weight,
+                                    dgamma_out=sink.get(b2.weight), dbeta_out=sink.get(b2.bias))
+    grads[c2.weight] = ops.conv3x3_wgrad(dz2, sv["a1"], dc.out_ch, out=sink.get(c2.weight))
+    # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
+    grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
     grads[b2.weight], grads[b2.bias] = dg2, db2
-    w2d = dc._cache().get(("wd", 3), [c2.weight], lambda: ops.pack_conv_weight(c2.weight, 1))
-    da1 = ops.conv3x3(dz2, w2d, dc.out_ch)["y"]
+    da1 = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad")["y"]
     del dz2
-    dz1, dg1, db1 = ops.bn_relu_bwd(sv["z1"], None, da1, False, None, *sv["s1"], b1.weight)
+    dz1, dg1, db1 = ops.bn_relu_bwd(sv["z1"], None, da1, False, None, *sv["s1"], b1.weight,
+                                    dgamma_out=sink.get(b1.weight), dbeta_out=sink.get(b1.bias))
     del da1
-    grads[c1.weight] = ops.conv3x3_wgrad(dz1, sv["x"], dc.in_ch)
-    grads[c1.bias] = torch.zeros_like(c1.bias)
+    grads[c1.weight] = ops.conv3x3_wgrad(dz1, sv["x"], dc.in_ch, out=sink.get(c1.weight))
+    grads[c1.bias] = sink[c1.bias] if c1.bias in sink else torch.zeros_like(c1.bias)
     grads[b1.weight], grads[b1.bias] = dg1, db1
     if not need_dx:
         return None
-    w1d = dc._cache().get(("wd", 0), [c1.weight], lambda: ops.pack_conv_weight(c1.weight, 1))
-    return ops.conv3x3(dz1, w1d, sv["x"].shape[4])["y"]
+    return ops.conv3x3(dz1, dc._packed_dgrad(0), sv["x"].shape[4], tag="dgrad")["y"]
 
 
 class _BiDateNetTrain(torch.autograd.Function):
@@ -89,34 +99,113 @@ class _BiDateNetTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         model, sv, params = ctx.model, ctx.sv, ctx.params
+        dp = model.__dict__.get("_fb_dp")            # DataParallelStep that owns the gradients, if any
+        sink = dp.sink if dp is not None else None
+        done = dp.block_done if dp is not None else (lambda name: None)
         grads = {}
         dlogits = dlogits.contiguous().float()
         oc = model.outc.conv
-        du4, grads[oc.weight], grads[oc.bias] = ops.outconv_bwd(dlogits, sv["up4"]["a2"], oc.weight)
-        # decoder, top down: d(cat) = [d(skip product) | d(upsampled low)]
-        dcat4 = _dc_backward(model.up4.conv, sv["up4"], du4, False, None, True, grads)
-        e1 = sv["inc"]["a2"]
-        du3 = ops.up_input_bwd(dcat4, e1.shape[4], e1.shape[2] // 2, e1.shape[3] // 2)
-        dcat3 = _dc_backward(model.up3.conv, sv["up3"], du3, False, None, True, grads)
-        e2 = sv["down1"]["a2"]
-        du2 = ops.up_input_bwd(dcat3, e2.shape[4], e2.shape[2] // 2, e2.shape[3] // 2)
-        dcat2 = _dc_backward(model.up2.conv, sv["up2"], du2, False, None, True, grads)
-        e3 = sv["down2"]["a2"]
-        du1 = ops.up_input_bwd(dcat2, e3.shape[4], e3.shape[2] // 2, e3.shape[3] // 2)
-        dcat1 = _dc_backward(model.up1.conv, sv["up1"], du1, False, None, True, grads)
-        e4 = sv["down3"]["a2"]
-        dp5 = ops.up_input_bwd(dcat1, e4.shape[4], e4.shape[2] // 2, e4.shape[3] // 2)   # d relu(x5_d2 * x5_d1)
-        # encoder, bottom up: each level's output gets the product-fusion gradient (times the other date's
-        # activation) plus the gradient flowing back through the max pool from the level below
-        gp4 = _dc_backward(model.down4.mpconv[1], sv["down4"], dp5, True, None, True, grads)
-        gp3 = _dc_backward(model.down3.mpconv[1], sv["down3"], dcat1, True, gp4, True, grads)
-        gp2 = _dc_backward(model.down2.mpconv[1], sv["down2"], dcat2, True, gp3, True, grads)
-        gp1 = _dc_backward(model.down1.mpconv[1], sv["down1"], dcat3, True, gp2, True, grads)
-        _dc_backward(model.inc.conv, sv["inc"], dcat4, True, gp1, False, grads)
+        with torch.cuda.device(dlogits.device):
+            s = sink or {}
+            du4, grads[oc.weight], grads[oc.bias] = ops.outconv_bwd(dlogits, sv["up4"]["a2"], oc.weight,
+                                                                    dw_out=s.get(oc.weight), db_out=s.get(oc.bias))
+            done("outc")
+            # decoder, top down: d(cat) = [d(skip product) | d(upsampled low)]
+            dcat4 = _dc_backward(model.up4.conv, sv["up4"], du4, False, None, True, grads, sink)
+            done("up4")
+            e1 = sv["inc"]["a2"]
+            du3 = ops.up_input_bwd(dcat4, e1.shape[4], e1.shape[2] // 2, e1.shape[3] // 2)
+            dcat3 = _dc_backward(model.up3.conv, sv["up3"], du3, False, None, True, grads, sink)
+            done("up3")
+            e2 = sv["down1"]["a2"]
+            du2 = ops.up_input_bwd(dcat3, e2.shape[4], e2.shape[2] // 2, e2.shape[3] // 2)
+            dcat2 = _dc_backward(model.up2.conv, sv["up2"], du2, False, None, True, grads, sink)
+            done("up2")
+            e3 = sv["down2"]["a2"]
+            du1 = ops.up_input_bwd(dcat2, e3.shape[4], e3.shape[2] // 2, e3.shape[3] // 2)
+            dcat1 = _dc_backward(model.up1.conv, sv["up1"], du1, False, None, True, grads, sink)
+            done("up1")
+            e4 = sv["down3"]["a2"]
+            dp5 = ops.up_input_bwd(dcat1, e4.shape[4], e4.shape[2] // 2, e4.shape[3] // 2)   # d relu(x5_d2 * x5_d1)
+            # encoder, bottom up: each level's output gets the product-fusion gradient (times the other date's
+            # activation) plus the gradient flowing back through the max pool from the level below
+            gp4 = _dc_backward(model.down4.mpconv[1], sv["down4"], dp5, True, None, True, grads, sink)
+            done("down4")
+            gp3 = _dc_backward(model.down3.mpconv[1], sv["down3"], dcat1, True, gp4, True, grads, sink)
+            done("down3")
+            gp2 = _dc_backward(model.down2.mpconv[1], sv["down2"], dcat2, True, gp3, True, grads, sink)
+            done("down2")
+            gp1 = _dc_backward(model.down1.mpconv[1], sv["down1"], dcat3, True, gp2, True, grads, sink)
+            done("down1")
+            _dc_backward(model.inc.conv, sv["inc"], dcat4, True, gp1, False, grads, sink)
+            done("inc")
         ctx.sv = None
+        if sink is not None:
+            # the kernels wrote into the bucket views that ARE p.grad: nothing for torch to accumulate
+            return (None, None, None, None) + tuple(None if p in sink else grads.get(p) for p in params)
         return (None, None, None, None) + tuple(grads.get(p) for p in params)
 
 
 def bidatenet_train_forward(model, x_d1, x_d2, aug=None):
     params = tuple(model.parameters())
-    return _BiDateNetTrain.apply(model, x_d1.contiguous(), x_d2.contiguous(), aug, *params)
+    if not params:
+        raise RuntimeError(
+            "this BiDateNet has no parameters of its own: it is an nn.DataParallel replica (reference utils/helpers.py:335). "
+            "fabric_b200 runs one process per GPU -- drop the nn.DataParallel wrapper and use "
+            "fabric_b200.distributed.DataParallelStep under torchrun instead")
+    with torch.cuda.device(x_d1.device):
+        return _BiDateNetTrain.apply(model, x_d1.contiguous(), x_d2.contiguous(), aug, *params)
+
+
+class _DoubleConvTrain(torch.autograd.Function):
+    """One stand-alone ``double_conv`` in training mode with the reference's calling convention (NCHW fp32 in / out,
+    models/unet_parts.py:21-23): the per-block entry point of ``double_conv`` / ``inconv`` / ``down`` / ``up`` ``.forward``."""
+
+    @staticmethod
+    def forward(ctx, dc, x, *params):
+        with torch.cuda.device(x.device):
+            x5 = ops.pack_input(x.contiguous(), c_pad=ops.cpad(dc.in_ch)).unsqueeze(0)
+            a2, _, sv = _dc_forward(dc, x5, False)
+            ctx.dc, ctx.sv, ctx.params, ctx.cin = dc, sv, params, x.shape[1]
+            ctx.need_dx = x.requires_grad
+            return ops.unpack_output(a2[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        dc, sv, params = ctx.dc, ctx.sv, ctx.params
+        grads = {}
+        with torch.cuda.device(dy.device):
+            ga = ops.pack_input(dy.contiguous().float(), c_pad=dc.out_ch).unsqueeze(0)
+            need_dx = ctx.need_dx and dc.in_ch % 64 == 0       # the 13-band stem has no data gradient (its input is data)
+            dx5 = _dc_backward(dc, sv, ga, False, None, need_dx, grads, None)
+            dx = ops.unpack_output(dx5[0])[:, :ctx.cin].contiguous() if dx5 is not None else None
+        ctx.sv = None
+        return (None, dx) + tuple(grads.get(p) for p in params)
+
+
+def double_conv_train_forward(dc, x):
+    params = tuple(dc.parameters())
+    if not params:
+        raise RuntimeError("this block is an nn.DataParallel replica without parameters; see fabric_b200.distributed")
+    return _DoubleConvTrain.apply(dc, x, *params)
+
+
+class _OutconvTrain(torch.autograd.Function):
+    """stand-alone ``outconv`` (models/unet_parts.py:88-90) with gradients"""
+
+    @staticmethod
+    def forward(ctx, oc, x, weight, bias):
+        with torch.cuda.device(x.device):
+            u5 = ops.pack_input(x.contiguous(), c_pad=x.shape[1]).unsqueeze(0)
+            ctx.oc, ctx.u5 = oc, u5
+            return ops.outconv(u5, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        with torch.cuda.device(dlogits.device):
+            du5, dw, db = ops.outconv_bwd(dlogits.contiguous().float(), ctx.u5, ctx.oc.conv.weight)
+            return None, ops.unpack_output(du5[0]), dw, db
+
+
+def outconv_train_forward(oc, x):
+    return _OutconvTrain.apply(oc, x, oc.conv.weight, oc.conv.bias)

@@ -13,10 +13,10 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet_parts import down, outconv, up, inconv
+from .unet_parts import _CacheInvalidation, down, outconv, up, inconv
 
 
-class BiDateNet(nn.Module):
+class BiDateNet(_CacheInvalidation, nn.Module):
     def __init__(self, n_channels, n_classes):
         super(BiDateNet, self).__init__()
         if n_channels > 16:
@@ -34,6 +34,17 @@ class BiDateNet(nn.Module):
         self.outc = outconv(64, n_classes)
         self.fuse_head = True
         self.fuse_product = True
+
+    def __setstate__(self, state):
+        """a whole-model pickle written by the reference (train.py:222) has none of this repo's extra attributes"""
+        super().__setstate__(state)
+        self.__dict__.setdefault("fuse_head", True)
+        self.__dict__.setdefault("fuse_product", True)
+
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s.pop("_fb_dp", None)          # a DataParallelStep (process group, bucket) is not part of the model
+        return s
 
     def set_input_normalisation(self, mean, std):
         """Per-band mean / std of the loader's z-score (reference utils/dataloaders.py:94-99, constants in
@@ -119,7 +130,15 @@ class BiDateNet(nn.Module):
         if not x_d1.is_cuda:
             raise RuntimeError("fabric_b200.BiDateNet runs on sm_100 CUDA devices only (no CPU fallback); "
                                "call .cuda() on the model and inputs")
-        if self.training:
+        if getattr(self, "_is_replica", False) or next(self.parameters(), None) is None:
+            raise RuntimeError("this BiDateNet is an nn.DataParallel replica (reference utils/helpers.py:335 wraps the model): "
+                               "fabric_b200 runs one process per GPU -- drop the nn.DataParallel wrapper and use "
+                               "fabric_b200.distributed.DataParallelStep under torchrun")
+        if self.training and torch.is_grad_enabled():
             from .autograd import bidatenet_train_forward
             return bidatenet_train_forward(self, x_d1, x_d2, aug)
-        return self.forward_packed(self.pack_pair(x_d1, x_d2, aug))
+        if self.training:
+            raise RuntimeError("BiDateNet in .train() mode under torch.no_grad(): call .eval() for inference "
+                               "(batch-statistics BatchNorm without a backward pass is not a path the reference uses)")
+        with torch.cuda.device(x_d1.device):
+            return self.forward_packed(self.pack_pair(x_d1, x_d2, aug))

@@ -199,3 +199,58 @@ extern "C" int fabric_b200_sgd_step(const void* chunks, int n_chunks, float lr, 
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
+
+
+// ---- the whole optimizer side of a training step in ONE launch ------------------------------------------------------
+// Records of 64 bytes, one CTA each (<= 65536 elements):
+//   mode 0: p -= lr * grad_scale * g                                  (plain SGD, train.py:55,95)
+//   mode 1: p *= stats_scale                                          (BatchNorm running statistics after the SUM all-reduce)
+//   mode 2: mode 0 for a 3x3 conv weight [Cout][Cin][3][3] AND refresh of its packed bf16 copies: wf[Cout][9][CinPad]
+//           (forward operand) and wd[Cin][9][Cout] with flipped taps (data-gradient operand); `off` = element offset of
+//           this record inside the weight tensor.  Replaces the 35 pack_weight launches a training step used to make.
+namespace {
+struct StepChunk {
+  float* p;
+  const float* g;
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int n, mode, off, Cout, Cin, CinPad, pad0, pad1;
+};
+static_assert(sizeof(StepChunk) == 64, "record layout is part of the ABI (fabric_b200/distributed.py packs it)");
+
+__global__ void __launch_bounds__(256) train_step_update_kernel(const StepChunk* __restrict__ chunks, float lr_scaled,
+                                                                float stats_scale) {
+  const StepChunk c = chunks[blockIdx.x];
+  if (c.mode == 1) {
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) c.p[i] *= stats_scale;
+    return;
+  }
+  if (c.mode == 0) {
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) c.p[i] -= lr_scaled * c.g[i];
+    return;
+  }
+  const int k9 = c.Cin * 9;
+  for (int i = threadIdx.x; i < c.n; i += blockDim.x) {
+    const float v = c.p[i] - lr_scaled * c.g[i];
+    c.p[i] = v;
+    const int e = c.off + i;
+    const int co = e / k9, r = e - co * k9;
+    const int ci = r / 9, tap = r - ci * 9;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    c.wf[((size_t)co * 9 + tap) * c.CinPad + ci] = h;
+    c.wd[((size_t)ci * 9 + (8 - tap)) * c.Cout + co] = h;
+  }
+}
+}  // namespace
+
+extern "C" int fabric_b200_train_step_update(const void* chunks, int n_chunks, float lr, float grad_scale, float stats_scale,
+                                             void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!chunks || n_chunks < 1) return fail(FB_ERR_ARG, "no chunks");
+  train_step_update_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const StepChunk*>(chunks),
+                                                                       lr * grad_scale, stats_scale);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}

@@ -11,6 +11,43 @@ from typing import Optional
 import torch
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated: first-touch then places the staging buffers in that node's memory, and the threads that issue the copies
+    run next to it.  With eight ranks on a two-socket host, unbound ranks put every staging buffer on the node the
+    launcher happened to run on and the H2D streams of the far GPUs cross the socket interconnect.  Best effort (sysfs):
+    returns the node id, or None when the topology cannot be read / there is a single node."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return None
+        if cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class HostPipeline:
     """Reusable pinned staging + streams for ``predict_patches``."""
 

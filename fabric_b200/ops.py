@@ -34,11 +34,21 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _need_cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.FabricB200Error("fabric_b200 ops need CUDA tensors on an sm_100 device; there is no CPU path")
-        if t is not None and not t.is_contiguous():
+        if not t.is_contiguous():
             raise _lib.FabricB200Error("fabric_b200 ops need contiguous tensors")
+        # kernels, TMA descriptors and the stream all belong to the CURRENT device: a tensor living elsewhere would be
+        # reached through peer access (or fault).  Fail loudly instead (use torch.cuda.set_device / torch.cuda.device).
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.FabricB200Error(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}; wrap the call in "
+                                       "`with torch.cuda.device(t.device):` (fabric_b200 launches on the current device's stream)")
 
 
 def sm_count() -> int:
@@ -162,7 +172,8 @@ DEFAULT_TUNING = dict(n_tile=0, halo=-1, a_stages=0, b_stages=0, b_resident=-1, 
 def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False, pool: bool = False, stats: bool = False,
             head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None,
-            true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None, shift_in_acc: bool = False):
+            true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None, shift_in_acc: bool = False,
+            tag: Optional[str] = None):
     """3x3 pad-1 convolution on tcgen05 (see include/fabric_b200.h: fabric_b200_conv3x3).
 
     Returns a dict with ``y`` [G,B,H,W,cout] bf16 and optionally ``pool`` [G,B,H/2,W/2,cout],
@@ -216,7 +227,8 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
         e1.record()
         # algorithmic flops: true input channels (13, not the padded 16) -- SURVEY.md 8d
         cin_true = true_cin if true_cin is not None else cin
-        prof.append((f"{cin_true}->{cout}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * cout))
+        prof.append(((tag + " " if tag else "") + f"{cin_true}->{cout}@{h}x{w}xG{g}", e0, e1,
+                     2.0 * g * b * h * w * 9 * cin_true * cout))
     return res
 
 
@@ -319,28 +331,32 @@ def seg_loss_fwd_bwd(kind: str, logits: torch.Tensor, labels: torch.Tensor, alph
     return loss, dlogits
 
 
-def outconv_bwd(dlogits: torch.Tensor, u5: torch.Tensor, weight: torch.Tensor):
+def outconv_bwd(dlogits: torch.Tensor, u5: torch.Tensor, weight: torch.Tensor, dw_out=None, db_out=None):
+    """``dw_out`` [2,C,1,1] / ``db_out`` [2] fp32: write the parameter gradients there (e.g. views of the data-parallel
+    gradient bucket) instead of fresh tensors."""
     g, b, h, w, c = u5.shape
     lib = _lib.load()
+    _need_cuda(dlogits, u5, dw_out, db_out)
     ws = torch.empty(check(lib.fabric_b200_outconv_bwd_ws_floats(c), "outconv_bwd ws"), dtype=torch.float32, device=u5.device)
     du = torch.empty_like(u5)
-    dw = torch.empty((2, c), dtype=torch.float32, device=u5.device)
-    db = torch.empty((2,), dtype=torch.float32, device=u5.device)
+    dw = dw_out if dw_out is not None else torch.empty((2, c), dtype=torch.float32, device=u5.device)
+    db = db_out if db_out is not None else torch.empty((2,), dtype=torch.float32, device=u5.device)
     check(lib.fabric_b200_outconv_bwd(_p(dlogits), _p(u5), _p(weight.detach().reshape(2, c).contiguous()), _p(du), _p(dw),
                                       _p(db), _p(ws), g * b, h, w, c, _stream()), "outconv_bwd")
     _count(2)
     return du, dw.view(2, c, 1, 1), db
 
 
-def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma):
+def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma, dgamma_out=None, dbeta_out=None):
     """BatchNorm(train)+ReLU backward with fused product / max-pool adjoints (see include/fabric_b200.h).
     Returns (dz [G,B,H,W,C] bf16, dgamma [C], dbeta [C])."""
     g, b, h, w, c = z5.shape
     lib = _lib.load()
+    _need_cuda(z5, a5, ga, gp, dgamma_out, dbeta_out)
     ws = torch.empty(check(lib.fabric_b200_bn_bwd_ws_floats(g, c), "bn_bwd ws"), dtype=torch.float32, device=z5.device)
     dz = torch.empty_like(z5)
-    dgamma = torch.empty(c, dtype=torch.float32, device=z5.device)
-    dbeta = torch.empty(c, dtype=torch.float32, device=z5.device)
+    dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, dtype=torch.float32, device=z5.device)
+    dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, dtype=torch.float32, device=z5.device)
     ga_groups, ga_ch = (ga.shape[0], ga.shape[4]) if ga is not None else (1, c)
     check(lib.fabric_b200_bn_relu_bwd(_p(z5), _p(a5), _p(ga), ga_groups, ga_ch, int(mul_other), _p(gp), _p(scale), _p(shift),
                                       _p(mean), _p(invstd), _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws),
@@ -358,10 +374,12 @@ def up_input_bwd(dcat5: torch.Tensor, cs: int, h: int, w: int) -> torch.Tensor:
     return dlow
 
 
-def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: int = 0, wide=None) -> torch.Tensor:
-    """dW [Cout,Cin,3,3] fp32 = autograd weight gradient of conv3x3(x5, W) given dL/dz (tcgen05, split-K)."""
+def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: int = 0, wide=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW [Cout,Cin,3,3] fp32 = autograd weight gradient of conv3x3(x5, W) given dL/dz (tcgen05, split-K).  ``out``: write
+    the gradient there (e.g. a view of the data-parallel gradient bucket)."""
     lib = _lib.load()
-    _need_cuda(dz5, x5)
+    _need_cuda(dz5, x5, out)
     g, b, h, w, ca = dz5.shape
     cb = x5.shape[4]
     d = _lib.WgradDesc()
@@ -382,7 +400,8 @@ def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: in
     if prof is not None:
         e1.record()
         prof.append((f"wgrad {cin_true}->{ca}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * ca))
-    dw = torch.empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
+    dw = out if out is not None else torch.empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
+    assert dw.shape == (ca, cin_true, 3, 3) and dw.dtype == torch.float32
     check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
     _count(2)
     return dw
@@ -409,12 +428,16 @@ def gather_tiles(scene: torch.Tensor, origins: torch.Tensor, p: int, mean=None, 
 
 
 def argmax_metrics(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, want_mask: bool = True,
-                   counts: Optional[torch.Tensor] = None):
+                   counts: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None):
     """torch.max(logits,1) indices as uint8 [B,H,W] and (with labels) confusion counts (TP, FP, FN, TN) accumulated
-    into `counts` (uint64 [4], device)."""
-    _need_cuda(logits, labels, counts)
+    into `counts` (uint64 [4], device).  ``mask_out``: write the mask there (contiguous uint8 [B,H,W])."""
+    _need_cuda(logits, labels, counts, mask_out)
     b, _, h, w = logits.shape
-    mask = torch.empty((b, h, w), dtype=torch.uint8, device=logits.device) if want_mask else None
+    if mask_out is not None:
+        assert mask_out.shape == (b, h, w) and mask_out.dtype == torch.uint8
+        mask = mask_out
+    else:
+        mask = torch.empty((b, h, w), dtype=torch.uint8, device=logits.device) if want_mask else None
     if labels is not None:
         if counts is None:
             counts = torch.zeros(4, dtype=torch.int64, device=logits.device)

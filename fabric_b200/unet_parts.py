@@ -19,7 +19,15 @@ from . import ops
 
 
 class _PackCache:
-    """Packed bf16 weights and folded BN (scale, shift), rebuilt only when the source tensors change."""
+    """Packed bf16 weights and folded BN (scale, shift), rebuilt when the source tensors change.
+
+    The key is (data_ptr, _version, device) of every source tensor.  ``_version`` does NOT move for writes through
+    ``.data`` / raw kernels (``p.data.copy_``, EMA updates, ``dist.broadcast(t.data)``, this repo's fused SGD kernel), so
+    the cache is ALSO dropped on every event after which such a write is plausible: ``module.train()`` / ``.eval()``,
+    ``load_state_dict``, ``_apply`` (``.to`` / ``.cuda`` / ``.half``), and explicitly through ``invalidate_caches()``
+    (``DataParallelStep`` calls it after ``broadcast_parameters`` and after every fused optimizer step).  A training-mode
+    forward never trusts the cache at all: weights change every step, so it repacks (or uses the packed copies the fused
+    optimizer kernel maintains, see ``fabric_b200.distributed``)."""
 
     def __init__(self):
         self._store = {}
@@ -33,8 +41,44 @@ class _PackCache:
         self._store[key] = (sig, val)
         return val
 
+    def clear(self):
+        self._store.clear()
 
-class double_conv(nn.Module):
+
+class _CacheInvalidation:
+    """Mixin for the block modules: drop packed-weight caches whenever the parameters may have been rewritten."""
+
+    def invalidate_caches(self):
+        for m in self.modules():
+            c = m.__dict__.get("_fb_cache")
+            if c is not None:
+                c.clear()
+        return self
+
+    def train(self, mode=True):
+        self.invalidate_caches()
+        return super().train(mode)
+
+    def _apply(self, fn, *a, **kw):
+        self.invalidate_caches()
+        for m in self.modules():
+            m.__dict__.pop("_fb_managed", None)      # packed copies owned by a DataParallelStep point at the old storage
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        r = super().load_state_dict(*a, **kw)
+        self.invalidate_caches()
+        return r
+
+    def _load_from_state_dict(self, *a, **kw):        # also reached when a PARENT module's load_state_dict recurses
+        r = super()._load_from_state_dict(*a, **kw)
+        c = self.__dict__.get("_fb_cache")
+        if c is not None:
+            c.clear()
+        return r
+
+
+class double_conv(_CacheInvalidation, nn.Module):
     '''(conv => BN => ReLU) * 2   -- reference models/unet_parts.py:8-23'''
 
     def __init__(self, in_ch, out_ch):
@@ -67,11 +111,39 @@ class double_conv(nn.Module):
     def __getstate__(self):
         s = dict(self.__dict__)
         s.pop("_fb_cache", None)
+        s.pop("_fb_managed", None)
         return s
 
-    def _packed(self, idx):
+    def __setstate__(self, state):
+        """Whole-model pickles written by the REFERENCE (train.py:222 ``torch.save(model)``) resolve to this class through
+        the ``models/`` shim but carry only the reference's attributes: derive the rest."""
+        super().__setstate__(state)
+        conv = self.__dict__["_modules"]["conv"]
+        d = self.__dict__
+        d.setdefault("in_ch", conv[0].weight.shape[1])
+        d.setdefault("out_ch", conv[0].weight.shape[0])
+        d.setdefault("tune1", None)
+        d.setdefault("tune2", None)
+        d.setdefault("fold_bn", True)
+
+    def _packed(self, idx, training=False):
+        """bf16 [Cout][9][CinPad] forward weights of conv ``idx``.  Training forwards never trust the version-keyed cache
+        (see _PackCache): they use the copies the fused optimizer kernel keeps fresh, else repack."""
         conv = self.conv[idx]
+        managed = self.__dict__.get("_fb_managed")
+        if managed is not None and managed.get(("v", idx)) == conv.weight._version:
+            return managed[("w", idx)]       # (a torch optimizer that updated the weight bumps _version: not ours any more)
+        if training:
+            return ops.pack_conv_weight(conv.weight, 0)
         return self._cache().get(("w", idx), [conv.weight], lambda: ops.pack_conv_weight(conv.weight, 0))
+
+    def _packed_dgrad(self, idx):
+        """bf16 [Cin][9][Cout] tap-flipped weights: conv3x3 with them is the data gradient of conv ``idx``"""
+        conv = self.conv[idx]
+        managed = self.__dict__.get("_fb_managed")
+        if managed is not None and managed.get(("v", idx)) == conv.weight._version:
+            return managed[("wd", idx)]
+        return ops.pack_conv_weight(conv.weight, 1)
 
     def _folded(self, idx):
         conv, bn = self.conv[idx], self.conv[idx + 1]
@@ -92,7 +164,8 @@ class double_conv(nn.Module):
         bias and ReLU ride in the conv epilogue; ``pool`` adds the fused MaxPool2d(2) copy for the next ``down``;
         ``head`` = (weight[2,64], bias[2]) fuses ``outconv`` into the second conv."""
         if self.training:
-            raise NotImplementedError("training-mode forward goes through fabric_b200.autograd (double_conv_train)")
+            raise RuntimeError("run5 is the eval fast path; training goes through fabric_b200.autograd "
+                               "(BiDateNet.forward / double_conv.forward in .train() mode)")
         if getattr(self, "fold_bn", True):
             w1, h1 = self._packed_folded(0)
             w2, h2 = self._packed_folded(3)
@@ -107,12 +180,20 @@ class double_conv(nn.Module):
                            store_main=keep_main, tune=self.tune2, prod_out=prod_out)
 
     def forward(self, x):
-        x5 = ops.pack_input(x, c_pad=ops.cpad(self.in_ch)).unsqueeze(0)
-        y = self.run5(x5)["y"]
-        return ops.unpack_output(y[0])
+        """reference models/unet_parts.py:21-23: NCHW fp32 in / out; differentiable in training mode (batch statistics,
+        running-stat update, gradients for x and all parameters)"""
+        if not x.is_cuda:
+            raise RuntimeError("fabric_b200 blocks run on sm_100 CUDA devices only (no CPU fallback)")
+        if self.training:
+            from .autograd import double_conv_train_forward
+            return double_conv_train_forward(self, x)
+        with torch.cuda.device(x.device):
+            x5 = ops.pack_input(x, c_pad=ops.cpad(self.in_ch)).unsqueeze(0)
+            y = self.run5(x5)["y"]
+            return ops.unpack_output(y[0])
 
 
-class inconv(nn.Module):
+class inconv(_CacheInvalidation, nn.Module):
     '''reference models/unet_parts.py:26-33'''
 
     def __init__(self, in_ch, out_ch):
@@ -127,7 +208,7 @@ class inconv(nn.Module):
         return x
 
 
-class down(nn.Module):
+class down(_CacheInvalidation, nn.Module):
     '''MaxPool2d(2) => double_conv   -- reference models/unet_parts.py:36-46.
     On the fast path the pooling is done by the PREVIOUS block's conv epilogue (``pool=True``), so ``run5``
     takes the already pooled tensor.'''
@@ -143,15 +224,11 @@ class down(nn.Module):
         return self.mpconv[1].run5(pooled5, **kw)
 
     def forward(self, x):
-        # standalone use: pool on the packed tensor with the same kernel path (pack -> pool via torch on bf16)
-        x5 = ops.pack_input(x, c_pad=ops.cpad(self.mpconv[1].in_ch))
-        b, h, w, c = x5.shape
-        x5 = x5[:, :h // 2 * 2, :w // 2 * 2].reshape(b, h // 2, 2, w // 2, 2, c).amax(dim=(2, 4)).contiguous()
-        y = self.mpconv[1].run5(x5.unsqueeze(0))["y"]
-        return ops.unpack_output(y[0])
+        # stand-alone use (reference :44-46): the pooling glue is torch's (differentiable), the double_conv is ours
+        return self.mpconv[1](torch.nn.functional.max_pool2d(x, 2))
 
 
-class up(nn.Module):
+class up(_CacheInvalidation, nn.Module):
     '''bilinear x2 => pad => cat([skip, up]) => double_conv   -- reference models/unet_parts.py:49-80'''
 
     def __init__(self, in_ch, out_ch, bilinear=True):
@@ -172,18 +249,15 @@ class up(nn.Module):
         return self.conv.run5(cat5, **kw)
 
     def forward(self, x1, x2):
-        # reference calling convention: x1 = low-res tensor, x2 = (already fused) skip, both NCHW fp32
-        low5 = ops.pack_input(x1).unsqueeze(0)
-        s = ops.pack_input(x2)
-        ones = torch.ones_like(s)
-        skip5 = torch.stack([s, ones])      # skip * 1, relu is a no-op only for non-negative skips
-        if bool((x2 < 0).any()):
-            raise NotImplementedError("standalone up.forward expects a non-negative (post-ReLU) skip tensor")
-        y = self.run5(low5, skip5)["y"]
-        return ops.unpack_output(y[0])
+        """reference calling convention (:64-80): x1 = low-res tensor, x2 = skip, both NCHW fp32.  Stand-alone use: the
+        upsample / pad / concat glue is torch's (differentiable); the double_conv runs on the tcgen05 kernels."""
+        x1 = self.up(x1)
+        dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
+        x1 = torch.nn.functional.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return self.conv(torch.cat([x2, x1], dim=1))
 
 
-class outconv(nn.Module):
+class outconv(_CacheInvalidation, nn.Module):
     '''1x1 conv head   -- reference models/unet_parts.py:83-90'''
 
     def __init__(self, in_ch, out_ch):
@@ -201,5 +275,11 @@ class outconv(nn.Module):
         return ops.outconv(x5, self.conv.weight, self.conv.bias)
 
     def forward(self, x):
-        x5 = ops.pack_input(x, c_pad=x.shape[1]).unsqueeze(0)
-        return self.run5(x5)
+        if not x.is_cuda:
+            raise RuntimeError("fabric_b200 blocks run on sm_100 CUDA devices only (no CPU fallback)")
+        if self.training and torch.is_grad_enabled():
+            from .autograd import outconv_train_forward
+            return outconv_train_forward(self, x)
+        with torch.cuda.device(x.device):
+            x5 = ops.pack_input(x, c_pad=x.shape[1]).unsqueeze(0)
+            return self.run5(x5)

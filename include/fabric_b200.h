@@ -243,6 +243,18 @@ int fabric_b200_scatter_tiles(const uint8_t* masks, const int* origins, uint8_t*
  * single NCCL all-reduce. */
 int fabric_b200_sgd_step(const void* chunks, int n_chunks, float lr, float grad_scale, void* stream);
 
+/* The whole optimizer side of one training step in ONE launch (reference train.py:95 `optimizer.step()` plus what
+ * nn.DataParallel's per-forward replica broadcast implies for the BatchNorm buffers).  `chunks` is a DEVICE array of
+ * n_chunks 64-byte records, one CTA each (<= 65536 elements):
+ *   { float* p; const float* g; bf16* wf; bf16* wd; int32 n, mode, off, Cout, Cin, CinPad, pad, pad }
+ *   mode 0: p -= lr * grad_scale * g
+ *   mode 1: p *= stats_scale             (running statistics living in the SUM-all-reduced bucket)
+ *   mode 2: mode 0 for elements [off, off+n) of a conv weight [Cout][Cin][3][3], and the same new values written as bf16
+ *           into its packed copies wf[Cout][9][CinPad] (fabric_b200_pack_conv3x3_weight mode 0) and wd[Cin][9][Cout]
+ *           (mode 1), so that the next step launches no pack kernels. */
+int fabric_b200_train_step_update(const void* chunks, int n_chunks, float lr, float grad_scale, float stats_scale,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,21 +25,97 @@ from oracle import bidatenet_oracle as O  # noqa: E402
 
 
 def load_reference():
-    # the reference's package is called `models` / `utils`: import it under its own names
-    # from its own directory (this repo's look-alike `models` package must not shadow it).
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")
-             or k == "utils" or k.startswith("utils.")}
-    sys.path.insert(0, REF)
-    try:
-        from models.bidate_model import BiDateNet            # noqa
-        from utils import metrics as ref_metrics              # noqa
-    finally:
-        sys.path.remove(REF)
-        for k in list(sys.modules):
-            if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils."):
-                sys.modules.pop(k)
-        sys.modules.update(saved)
+    """the reference's own modules, loaded by file path under private names (oracle/ref_loader.py): this repo's
+    ``models/`` pickle shim is a regular package and would shadow the reference's namespace package on sys.path"""
+    from oracle import ref_loader
+    BiDateNet, ref_metrics, _, root = ref_loader.load()
     return BiDateNet, ref_metrics
+
+
+def load_reference_host_side():
+    """utils/dataloaders.py and utils/inference.py of the reference, loaded by file path with their unavailable
+    imports stubbed (rasterio, cv2, utils.helpers: IO / plotting only) and the removed sklearn
+    ``image.extract_patches`` mapped to its surviving private twin ``_extract_patches`` (same function, renamed in
+    scikit-learn 0.24).  Only the pure-numpy functions are used: ``onera_siamese_loader``, ``_get_patches``,
+    ``_get_bands``."""
+    import importlib.util
+    import types
+    from sklearn.feature_extraction import image as sk_image
+    if not hasattr(sk_image, "extract_patches"):
+        sk_image.extract_patches = sk_image._extract_patches
+    saved = {k: sys.modules.get(k) for k in ("rasterio", "cv2", "utils", "utils.dataloaders", "utils.helpers")}
+    try:
+        for name in ("rasterio", "cv2"):
+            if saved[name] is None:
+                try:
+                    __import__(name)
+                except Exception:
+                    sys.modules[name] = types.ModuleType(name)
+        pkg = types.ModuleType("utils")
+        pkg.__path__ = []
+        sys.modules["utils"] = pkg
+        helpers = types.ModuleType("utils.helpers")
+        helpers.log_figure = helpers.scale = None
+        sys.modules["utils.helpers"] = helpers
+
+        def load(name, rel):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            return mod
+        dl = load("utils.dataloaders", "utils/dataloaders.py")
+        inf = load("utils.inference", "utils/inference.py")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return dl, inf
+
+
+def check_host_side():
+    """oracle tiler / reassembler / augmentation == the reference's numpy code (inference.py:134-236,
+    dataloaders.py:148-165), bit-exact, including ragged scene sizes and every (rot, flip, flip) combination."""
+    import random
+    dl, inf = load_reference_host_side()
+    rng = np.random.RandomState(7)
+    for (h, w, p) in ((64, 64, 32), (70, 97, 32), (96, 64, 32), (33, 47, 16), (48, 48, 16)):
+        bands = rng.randn(h, w, 13).astype(np.float32)
+        ref = inf._get_patches(bands, p)
+        ora = O.get_patches(bands, p)
+        assert np.array_equal(ref[0], ora[0]) and tuple(ref[1:]) == tuple(ora[1:]), (h, w, p)
+        masks = rng.randint(0, 2, size=(ref[0].shape[0], p, p)).astype(np.float64)
+        a = inf._get_bands(masks, *ref[1:], patch_size=p)
+        b = O.get_bands(masks, *ora[1:], patch_size=p)
+        assert np.array_equal(a, b), (h, w, p)
+    # augmentation: replay the loader's three random draws (randint(0,3), random(), random()) from the same seed
+    size = 12
+    img = rng.randn(2, 13, 40, 40).astype(np.float32)
+    lbl = rng.randint(0, 2, size=(40, 40)).astype(np.uint8)
+    dataset = {"c": {"images": img, "labels": lbl}}
+    seen = set()
+    for seed in range(64):
+        random.seed(seed)
+        rot = random.randint(0, 3)
+        f0 = random.random() > 0.5
+        f1 = random.random() > 0.5
+        random.seed(seed)
+        d1, d2, lab = dl.onera_siamese_loader(dataset, "c", 5, 9, size, True)
+        oi, ol = O.augment_patch(img[:, :, 5:5 + size, 9:9 + size], lbl[5:5 + size, 9:9 + size], rot, f0, f1)
+        assert np.array_equal(d1, oi[0]) and np.array_equal(d2, oi[1]) and np.array_equal(lab, ol), seed
+        # the gather form used by the device kernel
+        src = img[0, 0, 5:5 + size, 9:9 + size]
+        for (i, j) in ((0, 0), (3, 7), (size - 1, 2)):
+            si, sj = O.augment_source_index(i, j, size, rot, f0, f1)
+            assert d1[0, i, j] == src[si, sj], (seed, i, j)
+        seen.add((rot, f0, f1))
+    assert len(seen) == 16, "not every augmentation combination was exercised"
+    d1, d2, lab = dl.onera_siamese_loader(dataset, "c", 5, 9, size, False)
+    oi, ol = O.augment_patch(img[:, :, 5:5 + size, 9:9 + size], lbl[5:5 + size, 9:9 + size], 0, False, False)
+    assert np.array_equal(d1, oi[0]) and np.array_equal(lab, ol)
+    return len(seen)
 
 
 def ref_model(BiDateNet, sd):
@@ -49,11 +125,9 @@ def ref_model(BiDateNet, sd):
     return m
 
 
-def main():
-    torch.set_num_threads(os.cpu_count())
+def build_golden():
+    """Assert oracle == reference on every check and return what the REFERENCE produced (the golden dict)."""
     BiDateNet, RM = load_reference()
-    out_dir = os.path.join(ROOT, "tests", "golden")
-    os.makedirs(out_dir, exist_ok=True)
 
     # state_dict spec must equal the reference's, key for key
     ref_sd = BiDateNet(13, 2).state_dict()
@@ -161,9 +235,24 @@ def main():
         golden["sd_sum/" + k] = sd[k].double().sum()
         golden["sd_abssum/" + k] = sd[k].double().abs().sum()
 
-    torch.save(golden, os.path.join(out_dir, "bidatenet_golden.pt"))
-    sz = os.path.getsize(os.path.join(out_dir, "bidatenet_golden.pt"))
-    print(f"oracle == reference on all checks; wrote {len(golden)} tensors, {sz/1e6:.2f} MB")
+    return golden
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    golden = build_golden()
+    n_aug = check_host_side()
+    path = os.path.join(out_dir, "bidatenet_golden.pt")
+    if os.path.exists(path):
+        old = torch.load(path)
+        same = set(old) == set(golden) and all(torch.equal(torch.as_tensor(old[k]), torch.as_tensor(golden[k])) for k in golden)
+        print(f"committed fixture {'is reproduced bit-for-bit' if same else 'DIFFERS from this run'} ({len(old)} tensors)")
+    torch.save(golden, path)
+    sz = os.path.getsize(path)
+    print(f"oracle == reference on all checks (network, losses, training step, tiler, {n_aug} augmentations); "
+          f"wrote {len(golden)} tensors, {sz/1e6:.2f} MB")
 
 
 if __name__ == "__main__":

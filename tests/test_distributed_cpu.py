@@ -53,3 +53,83 @@ def test_data_parallel_step_world2_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_scene_plan_bands_partition_rows_and_reproduce_reference_reassembly():
+    """ScenePlan (config 5 row-band sharding): bands are disjoint and cover every row; composing each band from its own
+    tiles in the reference's overwrite order and concatenating equals the reference `_get_bands` on the full tile list."""
+    import numpy as np
+    from fabric_b200.scene import ScenePlan, tile_origins
+    from oracle import bidatenet_oracle as O
+    rng = np.random.RandomState(0)
+    for (h, w, p) in ((300, 200, 64), (70, 97, 32), (64, 64, 64), (129, 65, 32)):
+        bands13 = rng.randn(h, w, 13).astype(np.float32)
+        patches, hs, ws, lc, lr, _, _ = O.get_patches(bands13, p)
+        origins = tile_origins(h, w, p)[0]
+        tile_id = {o: i for i, o in enumerate(origins)}            # later duplicates (same origin) keep the LAST index
+        masks = np.stack([np.full((p, p), float(i % 251)) + rng.rand(p, p) for i in range(len(origins))])
+        want = O.get_bands(masks, hs, ws, lc, lr, h, w, patch_size=p)
+        for world in (1, 2, 3, 8):
+            rows, n = [], 0
+            for r in range(world):
+                plan = ScenePlan(h, w, p, r, world)
+                canvas = np.zeros((plan.band_rows, w))
+                first = 0
+                for cls_i, (f, cnt) in enumerate(plan.classes):
+                    for (y, x) in plan.origins_list[f:f + cnt]:
+                        gy = y + plan.row0
+                        # global tile index of this origin within its class (grid / last column / last row / corner)
+                        base = [0, hs * ws, hs * ws + lc, hs * ws + lc + lr][cls_i]
+                        k = {0: (gy // p) * ws + x // p, 1: gy // p, 2: x // p, 3: 0}[cls_i] + base
+                        assert origins[k] == (gy, x)
+                        canvas[y:y + p, x:x + p] = masks[k]
+                    n += cnt
+                rows.append(canvas)
+            assert n == len(origins)
+            assert np.array_equal(np.concatenate(rows, 0), want), (h, w, p, world)
+
+
+def test_reference_pickle_loads_through_the_shim(tmp_path):
+    """torch.save(model) as the reference does it (train.py:222), written with the REFERENCE's own classes registered
+    under their real module paths, resolves through this repo's `models/` shim to fabric_b200 classes whose extra
+    attributes are derived in __setstate__."""
+    import sys
+    import pytest
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference sources not reachable")
+    RefNet, _, parts, _ = ref_loader.load()
+    from oracle import bidatenet_oracle as O
+    ref = RefNet(13, 2)
+    ref.load_state_dict(O.make_state_dict(seed=0))
+    net_mod = sys.modules[RefNet.__module__]
+    saved = {k: sys.modules.get(k) for k in ("models", "models.bidate_model", "models.unet_parts")}
+    classes = [RefNet] + [getattr(parts, n) for n in ("double_conv", "inconv", "down", "up", "outconv")]
+    old_names = [c.__module__ for c in classes]
+    try:                                   # pickle the reference model exactly as train.py:222 would name its classes
+        import types
+        pkg = types.ModuleType("models"); pkg.__path__ = []
+        sys.modules.update({"models": pkg, "models.bidate_model": net_mod, "models.unet_parts": parts})
+        RefNet.__module__ = "models.bidate_model"
+        for c in classes[1:]:
+            c.__module__ = "models.unet_parts"
+        path = tmp_path / "reference_model.pt"
+        torch.save(ref, path)
+    finally:
+        for c, n in zip(classes, old_names):
+            c.__module__ = n
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    import models.bidate_model as shim                   # this repo's shim again
+    loaded = torch.load(path, weights_only=False)
+    from fabric_b200 import BiDateNet
+    from fabric_b200.unet_parts import double_conv
+    assert type(loaded) is BiDateNet is shim.BiDateNet
+    dcs = [m for m in loaded.modules() if isinstance(m, double_conv)]
+    assert len(dcs) == 9 and dcs[0].in_ch == 13 and dcs[0].out_ch == 64 and dcs[5].in_ch == 1024 and dcs[5].fold_bn
+    assert loaded.fuse_head and loaded.fuse_product
+    for k, v in ref.state_dict().items():
+        assert torch.equal(loaded.state_dict()[k], v), k

@@ -1,0 +1,551 @@
+"""GPU tests added in round 2 (run with -m gpu on a B200):
+
+* the training step at the BENCHMARK shape (64 pairs of 13x256x256): determinism, finiteness, exact linearity of the
+  backward in the upstream gradient, date-swap symmetry, teacher-forced gradients of one 256x256 pair vs fp32 autograd;
+* training at the reference's default geometry (patch 90, batch 32: metadata.json:32-33,40 -- the F.pad branch of `up`);
+* a short SGD trajectory against the fp32 oracle;
+* the data-parallel step: gradients written straight into the all-reduce bucket, the fused update kernel (SGD + running
+  statistics + packed-weight refresh) bit-equal to torch.optim.SGD + the pack kernels, 2-rank NCCL equivalence;
+* per-block train-mode entry points (double_conv / down / up / outconv .forward with gradients) vs torch;
+* cache invalidation after writes that do not bump tensor versions; scene row-band sharding; device guard.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from fabric_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def _model(cuda, seed=0, train=True):
+    from fabric_b200 import BiDateNet
+    from oracle import bidatenet_oracle as O
+    m = BiDateNet(13, 2)
+    m.load_state_dict(O.make_state_dict(seed=seed))
+    m = m.to(cuda)
+    return m.train() if train else m.eval()
+
+
+def _grads(model):
+    return {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+
+def _step(model, x1, x2, labels, scale=1.0):
+    from fabric_b200.metrics import TverskyLoss
+    for p in model.parameters():
+        p.grad = None
+    loss = TverskyLoss(alpha=0.1, beta=0.9)(model(x1, x2), labels)
+    (loss * scale).backward()
+    return loss.detach().clone()
+
+
+# ------------------------------------------------------------------------------------------------ benchmark shape
+def test_train_step_full_batch_properties(cuda):
+    """BASELINE configs[2] shape (64 x 13x256x256), properties that need no oracle at this size:
+    finite, deterministic (two runs bit-equal), backward exactly linear in the upstream gradient (x2 is exact in bf16 and
+    fp32), and date-swap symmetry (the network is symmetric in its two inputs: shared encoder, commutative fusion)."""
+    g = torch.Generator(device=cuda).manual_seed(11)
+    x1 = torch.randn(64, 13, 256, 256, device=cuda, generator=g)
+    x2 = torch.randn(64, 13, 256, 256, device=cuda, generator=g)
+    labels = (torch.rand(64, 256, 256, device=cuda, generator=g) < 0.1).long()
+    runs = []
+    for scale, swap in ((1.0, False), (1.0, False), (2.0, False), (1.0, True)):
+        model = _model(cuda)
+        loss = _step(model, x2 if swap else x1, x1 if swap else x2, labels, scale)
+        runs.append((loss, _grads(model), {k: v.clone() for k, v in model.state_dict().items() if "running" in k}))
+        del model
+    (l0, g0, s0), (l1, g1, s1), (l2, g2, _), (l3, g3, _) = runs
+    assert torch.isfinite(l0) and all(torch.isfinite(v).all() for v in g0.values())
+    assert 0.0 < float(l0) < 1.0
+    assert torch.equal(l0, l1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), f"not deterministic: {k}"
+        assert torch.equal(g2[k], 2 * g0[k]), f"backward not linear in the upstream gradient: {k}"
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
+    # swapped dates: same logits / loss; gradients equal up to the fp32 summation order of the two date groups
+    assert abs(float(l3) - float(l0)) <= 1e-6
+    for k in g0:
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            continue
+        assert rel(g3[k], g0[k]) <= 2e-3, (k, rel(g3[k], g0[k]))
+    # conv biases in front of a train-mode BatchNorm: exactly zero gradient; every other gradient is non-trivial
+    for k, v in g0.items():
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            assert float(v.abs().max()) == 0.0, k
+        else:
+            assert float(v.abs().max()) > 0.0, k
+
+
+@pytest.mark.parametrize("batch,size,seed", [(1, 256, 7), (3, 90, 11)])
+def test_backward_teacher_forced_at_benchmark_patch_and_reference_default_patch(cuda, batch, size, seed):
+    """fp32 torch autograd of the oracle graph evaluated AT the tensors the CUDA forward stored reproduces the CUDA
+    gradients at the benchmark patch size (256, one pair) and at the reference's default patch (90: odd sizes, the F.pad
+    branch of `up`, unet_parts.py:68-72).  Tolerance: rel-L2 <= 3e-2 per parameter tensor (bf16 activation gradients)."""
+    from fabric_b200 import autograd
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    from oracle import bidatenet_oracle_bf16 as Q
+    from tests.test_gpu_train import _saved_as_nchw
+    sd = O.make_state_dict(seed=0)
+    model = _model(cuda)
+    x1, x2, labels = O.make_inputs(batch, size, seed=seed)
+    autograd.KEEP_SAVED = True
+    try:
+        logits = model(x1.to(cuda), x2.to(cuda))
+        saved = _saved_as_nchw(autograd.LAST_SAVED)
+    finally:
+        autograd.KEEP_SAVED, autograd.LAST_SAVED = False, None
+    loss = TverskyLoss(alpha=0.1, beta=0.9)(logits, labels.to(cuda))
+    loss.backward()
+    for g in (0, 1):
+        saved[f"inc.x.{g}"] = saved[f"inc.x.{g}"][:, :13].contiguous()
+    loss_f, logits_f, grads_f = Q.train_step_forced(x1, x2, labels, sd, lambda l, t: O.tversky_loss(l, t, 0.1, 0.9), saved)
+    assert rel(logits.detach().cpu(), logits_f) <= 1e-4
+    assert abs(loss.item() - float(loss_f)) <= 1e-5
+    worst = (0.0, "")
+    for k, p in model.named_parameters():
+        if k.endswith(".0.bias") or k.endswith(".3.bias"):
+            continue
+        worst = max(worst, (rel(p.grad.detach().cpu(), grads_f[k]), k))
+    assert worst[0] <= 3e-2, worst
+
+
+def test_training_step_reference_default_geometry(cuda):
+    """patch 90, batch 32 (metadata.json:32-33,40): one full step vs the free-running fp32 oracle -- loss, train-mode
+    logits, BatchNorm running statistics -- plus determinism.  Batch statistics over 32 x 90 x 90 pixels are well
+    conditioned, so the fp32 reference is the yardstick here (logits rel-L2 <= 3e-2, conv weight gradients <= 0.1)."""
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    sd = O.make_state_dict(seed=0)
+    x1, x2, labels = O.make_inputs(32, 90, seed=21)
+    torch.set_num_threads(os.cpu_count())
+    l_o, logits_o, grads_o, new_o = O.train_step(x1, x2, labels, sd, lambda l, t: O.tversky_loss(l, t, 0.1, 0.9))
+    outs = []
+    for _ in range(2):
+        model = _model(cuda)
+        logits = model(x1.to(cuda), x2.to(cuda))
+        loss = TverskyLoss(alpha=0.1, beta=0.9)(logits, labels.to(cuda))
+        loss.backward()
+        outs.append((logits.detach().clone(), loss.detach().clone(), _grads(model), model.state_dict()))
+    logits, loss, grads, st = outs[0]
+    assert torch.equal(logits, outs[1][0]) and torch.equal(loss, outs[1][1])
+    assert all(torch.equal(grads[k], outs[1][2][k]) for k in grads)
+    assert rel(logits.cpu(), logits_o) <= 3e-2, rel(logits.cpu(), logits_o)
+    assert abs(float(loss) - float(l_o)) <= 2e-3
+    for k, v in new_o.items():
+        if "running" in k:
+            assert rel(st[k].cpu().float(), v.float()) <= 1e-2, k
+        if "num_batches" in k:
+            assert int(st[k]) == int(v), k
+    worst = (0.0, "")
+    for k, g in grads.items():
+        if g.dim() == 4:
+            worst = max(worst, (rel(g.cpu(), grads_o[k]), k))
+    assert worst[0] <= 0.1, worst
+
+
+def test_sgd_trajectory_follows_fp32_oracle(cuda):
+    """12 SGD steps (lr 0.05, Tversky) on a fixed batch of 8 pairs 13x64x64: the loss curve of the CUDA path stays within
+    1.5e-2 of the fp32 oracle's at every step and both decrease -- a systematic bias in the bf16 BatchNorm-backward or
+    weight-gradient path would show up as a diverging curve."""
+    from fabric_b200.distributed import DataParallelStep
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    lr, steps = 0.05, 12
+    sd = O.make_state_dict(seed=0)
+    x1, x2, labels = O.make_inputs(8, 64, seed=31)
+    crit_o = lambda l, t: O.tversky_loss(l, t, 0.1, 0.9)   # noqa: E731
+    cur = {k: v.clone() for k, v in sd.items()}
+    curve_o = []
+    for _ in range(steps):
+        l_o, _, grads_o, new_o = O.train_step(x1, x2, labels, cur, crit_o)
+        curve_o.append(float(l_o))
+        for k, g in grads_o.items():
+            cur[k] = cur[k] - lr * g
+        cur.update(new_o)
+    model = _model(cuda)
+    dp = DataParallelStep(model)
+    crit = TverskyLoss(alpha=0.1, beta=0.9)
+    a, b, lab = x1.to(cuda), x2.to(cuda), labels.to(cuda)
+    curve = []
+    for _ in range(steps):
+        dp.zero_grad()
+        loss = crit(model(a, b), lab)
+        loss.backward()
+        dp.sync_and_step(lr)
+        curve.append(float(loss))
+    print("oracle", [round(v, 4) for v in curve_o])
+    print("cuda  ", [round(v, 4) for v in curve])
+    assert curve_o[-1] < curve_o[0] - 0.02 and curve[-1] < curve[0] - 0.02
+    assert max(abs(u - v) for u, v in zip(curve, curve_o)) <= 1.5e-2, list(zip(curve, curve_o))
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel step
+def test_gradients_land_in_the_bucket_and_fused_update_matches_torch(cuda):
+    """DataParallelStep: p.grad is a view of the flat bucket and the backward kernels write there (no copies); the ONE
+    update kernel == torch.optim.SGD + pack_conv_weight for both packed layouts, bit for bit; a second step then uses the
+    refreshed packed copies (no pack launches) and equals a model that repacks from scratch."""
+    from fabric_b200 import ops
+    from fabric_b200.distributed import DataParallelStep
+    from oracle import bidatenet_oracle as O
+    x1, x2, labels = O.make_inputs(2, 32, seed=3)
+    x1, x2, labels = x1.to(cuda), x2.to(cuda), labels.to(cuda)
+    ref = _model(cuda)                                   # plain autograd Function + torch SGD
+    opt = torch.optim.SGD(ref.parameters(), lr=0.5)
+    l_ref = _step(ref, x1, x2, labels)
+    g_ref = _grads(ref)
+    opt.step()
+    model = _model(cuda)
+    dp = DataParallelStep(model)
+    for p in model.parameters():
+        assert p.grad.data_ptr() >= dp.bucket.data_ptr() and p.grad.data_ptr() < dp.bucket.data_ptr() + dp.bucket.numel() * 4
+    dp.zero_grad()
+    from fabric_b200.metrics import TverskyLoss
+    n0 = ops.LAUNCHES
+    loss = TverskyLoss(alpha=0.1, beta=0.9)(model(x1, x2), labels)
+    loss.backward()
+    assert torch.equal(loss.detach(), l_ref)
+    for k, p in model.named_parameters():
+        assert p.grad is dp.sink[p] and torch.equal(p.grad, g_ref[k]), k
+    dp.sync_and_step(0.5)
+    launches_step1 = ops.LAUNCHES - n0
+    for (k, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert torch.equal(p.detach(), q.detach()), k
+    for k, v in ref.state_dict().items():
+        assert torch.equal(model.state_dict()[k], v), k
+    # packed copies maintained by the update kernel == the pack kernels run on the new weights
+    from fabric_b200.unet_parts import double_conv
+    for m in model.modules():
+        if isinstance(m, double_conv):
+            for idx in (0, 3):
+                w = m.conv[idx].weight
+                assert torch.equal(m._packed(idx, training=True), ops.pack_conv_weight(w, 0)), idx
+                assert torch.equal(m._packed_dgrad(idx), ops.pack_conv_weight(w, 1)), idx
+    # second step: no pack kernels are launched and the result equals the reference model's second step
+    l_ref2 = _step(ref, x1, x2, labels)
+    n1 = ops.LAUNCHES
+    loss2 = TverskyLoss(alpha=0.1, beta=0.9)(model(x1, x2), labels)
+    loss2.backward()
+    dp.sync_and_step(0.5)
+    assert torch.equal(loss2.detach(), l_ref2)
+    assert ops.LAUNCHES - n1 == launches_step1
+    g_ref2 = _grads(ref)
+    for k, p in model.named_parameters():
+        assert torch.equal(p.grad, g_ref2[k]), k
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fabric_b200 import BiDateNet
+    from fabric_b200.distributed import DataParallelStep
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    model = BiDateNet(13, 2)
+    model.load_state_dict(O.make_state_dict(seed=rank))        # different weights per rank on purpose
+    model = model.to(dev).train()
+    dp = DataParallelStep(model)
+    dp.broadcast_parameters(0)
+    x1, x2, labels = O.make_inputs(2 * world, 32, seed=5)      # the global batch; rank r takes pairs [2r, 2r+2)
+    sl = slice(2 * rank, 2 * rank + 2)
+    crit = TverskyLoss(alpha=0.1, beta=0.9)
+    for _ in range(2):
+        dp.zero_grad()
+        loss = crit(model(x1[sl].to(dev), x2[sl].to(dev)), labels[sl].to(dev))
+        loss.backward()
+        dp.sync_and_step(0.25)
+    torch.cuda.synchronize()
+    out[rank] = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
+def test_data_parallel_step_nccl_two_ranks_equals_manual_average(cuda):
+    """Two NCCL ranks x 2 pairs, two steps of DataParallelStep (segmented async all-reduce + fused update) == one process
+    that runs both shards through the same kernels and applies p -= lr * mean_r(g_r) and mean_r(running stats)."""
+    import torch.multiprocessing as mp
+    from fabric_b200.metrics import TverskyLoss
+    from oracle import bidatenet_oracle as O
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = [out[r] for r in range(world)]
+    for k in got[0]:
+        assert torch.equal(got[0][k], got[1][k]), f"replicas diverged: {k}"
+    # manual emulation on one GPU
+    x1, x2, labels = O.make_inputs(2 * world, 32, seed=5)
+    crit = TverskyLoss(alpha=0.1, beta=0.9)
+    sd = O.make_state_dict(seed=0)
+    for _ in range(2):
+        grads, stats = [], []
+        for r in range(world):
+            m = _model(cuda)
+            m.load_state_dict(sd)
+            m.train()
+            sl = slice(2 * r, 2 * r + 2)
+            crit(m(x1[sl].to(cuda), x2[sl].to(cuda)), labels[sl].to(cuda)).backward()
+            grads.append({k: p.grad.detach().cpu() for k, p in m.named_parameters()})
+            stats.append({k: v.detach().cpu() for k, v in m.state_dict().items()})
+        new = {}
+        for k, v in sd.items():
+            if k in grads[0]:
+                new[k] = v - 0.25 * 0.5 * (grads[0][k] + grads[1][k])
+            elif "running" in k:
+                new[k] = 0.5 * (stats[0][k] + stats[1][k])
+            else:
+                new[k] = stats[0][k]
+        sd = new
+    for k, v in sd.items():
+        if v.dtype.is_floating_point:
+            assert torch.allclose(got[0][k], v, rtol=1e-5, atol=1e-7), k
+        else:
+            assert torch.equal(got[0][k], v), k
+
+
+# ------------------------------------------------------------------------------------------------ per-block entry points
+def _ref_double_conv(cin, cout, cuda):
+    m = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, 3, padding=1), torch.nn.BatchNorm2d(cout), torch.nn.ReLU(),
+                            torch.nn.Conv2d(cout, cout, 3, padding=1), torch.nn.BatchNorm2d(cout), torch.nn.ReLU()).to(cuda)
+    return m
+
+
+def _copy_dc(dst, src):
+    with torch.no_grad():
+        for i in (0, 1, 3, 4):
+            dst.conv[i].load_state_dict(src[i].state_dict())
+
+
+@pytest.mark.parametrize("block", ["double_conv", "down", "up", "inconv"])
+def test_block_train_mode_forward_backward_matches_torch(cuda, block):
+    """`double_conv` / `inconv` / `down` / `up` `.forward` in .train() mode (reference unet_parts.py:21-23,31-33,44-46,64-80):
+    outputs (batch statistics), running-stat updates and gradients for inputs and parameters vs the torch modules."""
+    from fabric_b200 import unet_parts as P
+    torch.manual_seed(4)
+    B, H, W = 3, 24, 40
+    if block == "double_conv":
+        mine, cin, cout = P.double_conv(64, 128), 64, 128
+        ref = _ref_double_conv(cin, cout, cuda)
+        _copy_dc(mine, ref)
+        args = (torch.randn(B, cin, H, W, device=cuda),)
+        ref_fn = lambda x: ref(x)                                      # noqa: E731
+    elif block == "inconv":
+        mine, cin, cout = P.inconv(13, 64), 13, 64
+        ref = _ref_double_conv(cin, cout, cuda)
+        _copy_dc(mine.conv, ref)
+        args = (torch.randn(B, cin, H, W, device=cuda),)
+        ref_fn = lambda x: ref(x)                                      # noqa: E731
+    elif block == "down":
+        mine, cin, cout = P.down(64, 128), 64, 128
+        ref = _ref_double_conv(cin, cout, cuda)
+        _copy_dc(mine.mpconv[1], ref)
+        args = (torch.randn(B, cin, 2 * H, 2 * W, device=cuda),)
+        ref_fn = lambda x: ref(F.max_pool2d(x, 2))                     # noqa: E731
+    else:
+        mine, cout = P.up(128, 64), 64
+        ref = _ref_double_conv(128, cout, cuda)
+        _copy_dc(mine.conv, ref)
+        args = (torch.randn(B, 64, H // 2, W // 2 - 1, device=cuda), torch.randn(B, 64, H, W, device=cuda).relu())
+
+        def ref_fn(x1, x2):
+            x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+            dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
+            x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+            return ref(torch.cat([x2, x1], dim=1))
+    mine = mine.to(cuda).train()
+    ref.train()
+    # bf16-representable inputs so that both sides see the same numbers
+    args = tuple(a.bfloat16().float().requires_grad_(block != "inconv") for a in args)
+    rargs = tuple(a.detach().clone().requires_grad_(block != "inconv") for a in args)
+    y = mine(*args)
+    yr = ref_fn(*rargs)
+    assert y.shape == yr.shape and rel(y, yr) <= 2e-2, rel(y, yr)
+    gy = torch.randn_like(yr).bfloat16().float()
+    y.backward(gy)
+    yr.backward(gy)
+    dc = mine if block == "double_conv" else (mine.mpconv[1] if block == "down" else mine.conv if block == "up" else mine.conv)
+    for i in (0, 3):
+        assert rel(dc.conv[i].weight.grad, ref[i].weight.grad) <= 4e-2, (i, rel(dc.conv[i].weight.grad, ref[i].weight.grad))
+        assert rel(dc.conv[i + 1].weight.grad, ref[i + 1].weight.grad) <= 6e-2
+        assert rel(dc.conv[i + 1].bias.grad, ref[i + 1].bias.grad) <= 6e-2
+        assert rel(dc.conv[i + 1].running_mean, ref[i + 1].running_mean) <= 1e-2
+        assert rel(dc.conv[i + 1].running_var, ref[i + 1].running_var) <= 1e-2
+    if block != "inconv":
+        for a, r in zip(args, rargs):
+            assert rel(a.grad, r.grad) <= 4e-2, rel(a.grad, r.grad)
+
+
+def test_outconv_train_mode_has_gradients(cuda):
+    from fabric_b200 import unet_parts as P
+    torch.manual_seed(5)
+    mine = P.outconv(64, 2).to(cuda).train()
+    ref = torch.nn.Conv2d(64, 2, 1).to(cuda)
+    ref.load_state_dict(mine.conv.state_dict())
+    x = torch.randn(2, 64, 20, 12, device=cuda).bfloat16().float().requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    y, yr = mine(x), ref(xr)
+    assert rel(y, yr) <= 1e-5
+    gy = torch.randn_like(yr)
+    y.backward(gy)
+    yr.backward(gy)
+    assert rel(mine.conv.weight.grad, ref.weight.grad) <= 1e-4 and rel(mine.conv.bias.grad, ref.bias.grad) <= 1e-5
+    assert rel(x.grad, xr.grad) <= 5e-3        # stored as bf16
+
+
+# ------------------------------------------------------------------------------------------------ caches / pickles / guard
+def test_caches_follow_writes_that_do_not_bump_versions(cuda):
+    """`.data` writes keep `_version`; the packed-weight / folded-BN caches must not serve stale weights after
+    load_state_dict, a train()/eval() round trip, `.to()`, or an explicit invalidate_caches()."""
+    from oracle import bidatenet_oracle as O
+    model = _model(cuda, train=False)
+    x1, x2, _ = O.make_inputs(2, 32, seed=9)
+    x1, x2 = x1.to(cuda), x2.to(cuda)
+    with torch.no_grad():
+        y0 = model(x1, x2).clone()
+        w = model.down2.mpconv[1].conv[0].weight
+        v0 = w._version
+        w.data.mul_(1.5)                                  # no version bump
+        assert w._version == v0
+        model.invalidate_caches()
+        y1 = model(x1, x2).clone()
+        assert not torch.equal(y0, y1)
+        model.up1.conv.conv[4].running_var.data.mul_(2.0)
+        model.train(); model.eval()                        # mode round trip drops the caches too
+        y2 = model(x1, x2).clone()
+        assert not torch.equal(y1, y2)
+        model.load_state_dict(O.make_state_dict(seed=0))   # same tensors, new values, in place
+        assert torch.equal(model(x1, x2), y0)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ref = O.bidatenet_forward(x1.cpu(), x2.cpu(), sd, training=False)
+    assert rel(y0.cpu(), ref) <= 1e-2
+
+
+def test_reference_style_pickle_runs(cuda, tmp_path):
+    """a whole-model pickle carrying only the REFERENCE's attributes (train.py:222) loads through the models/ shim and runs
+    in eval and train mode (the extra attributes of this repo's classes are derived in __setstate__)"""
+    from fabric_b200 import BiDateNet
+    from fabric_b200.unet_parts import double_conv
+    from oracle import bidatenet_oracle as O
+    m = BiDateNet(13, 2)
+    m.load_state_dict(O.make_state_dict(seed=0))
+    for mod in m.modules():                                # strip everything the reference's classes do not have
+        for name in ("in_ch", "out_ch", "tune1", "tune2", "fold_bn", "fuse_head", "fuse_product"):
+            mod.__dict__.pop(name, None)
+    path = tmp_path / "ref_style.pt"
+    torch.save(m, path)
+    m2 = torch.load(path, weights_only=False).to(cuda).eval()
+    assert all(hasattr(d, "in_ch") for d in m2.modules() if isinstance(d, double_conv))
+    x1, x2, labels = O.make_inputs(2, 32, seed=1)
+    with torch.no_grad():
+        y = m2(x1.to(cuda), x2.to(cuda))
+    ref = O.bidatenet_forward(x1, x2, O.make_state_dict(seed=0), training=False)
+    assert rel(y.cpu(), ref) <= 1e-2
+    m2.train()
+    from fabric_b200.metrics import dice_loss
+    dice_loss(m2(x1.to(cuda), x2.to(cuda)), labels.to(cuda)).backward()
+    assert all(p.grad is not None for p in m2.parameters())
+
+
+def test_dataparallel_replica_is_rejected_with_a_pointer(cuda):
+    """nn.DataParallel replicas have no parameters of their own (reference helpers.py:335 wraps the model): the forward must
+    say what to use instead, not fail deep inside autograd"""
+    model = _model(cuda)
+    replica = model._replicate_for_data_parallel()
+    with pytest.raises(RuntimeError, match="DataParallelStep"):
+        replica(torch.zeros(1, 13, 32, 32, device=cuda), torch.zeros(1, 13, 32, 32, device=cuda))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tensor_on_another_device_is_rejected(cuda):
+    from fabric_b200 import _lib, ops
+    x = torch.zeros(1, 13, 32, 32, device="cuda:1")
+    with pytest.raises(_lib.FabricB200Error, match="current device"):
+        ops.pack_input(x)
+    with torch.cuda.device(1):
+        assert ops.pack_input(x).device.index == 1
+
+
+# ------------------------------------------------------------------------------------------------ scene bands
+def test_scene_row_bands_concatenate_to_the_single_rank_mask(cuda):
+    """config 5 sharding: ranks own disjoint row bands; each band computed from ONLY its scene rows; the concatenation of
+    the bands equals the single-rank mask, which equals the reference pipeline's (existing test)."""
+    from fabric_b200.scene import ScenePlan, predict_scene, predict_scene_band
+    model = _model(cuda, train=False)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    H, W, p = 300, 200, 64
+    d1 = torch.randn(13, H, W, device=cuda, generator=g)
+    d2 = torch.randn(13, H, W, device=cuda, generator=g)
+    full, info = predict_scene(model, d1, d2, patch_size=p, batch_size=7)
+    assert info["tiles"] == 4 * 3 + 4 + 3 + 1
+    for world in (2, 3, 5):
+        bands = []
+        for r in range(world):
+            plan = ScenePlan(H, W, p, r, world)
+            bands.append(predict_scene_band(model, d1[:, plan.row0:plan.row1].contiguous(), d2[:, plan.row0:plan.row1].contiguous(),
+                                            plan, batch_size=5))
+        assert torch.equal(torch.cat(bands, 0), full), world
+
+
+def test_step_update_kernel_modes(cuda):
+    """fabric_b200_train_step_update: mode 0 (SGD), mode 1 (scale), mode 2 (SGD + packed refresh incl. the 13 -> 16 padded stem)"""
+    import struct
+    from fabric_b200 import _lib, ops
+    torch.manual_seed(6)
+    w = torch.randn(64, 13, 3, 3, device=cuda)
+    gw = torch.randn_like(w)
+    b = torch.randn(100000, device=cuda)
+    gb = torch.randn_like(b)
+    st = torch.randn(777, device=cuda)
+    wf, wd = ops.pack_conv_weight(w, 0), ops.pack_conv_weight(w, 1)
+    w0, b0, st0 = w.clone(), b.clone(), st.clone()
+    recs, n = bytearray(), 0
+
+    def emit(p, g, cnt, mode, f=0, d=0, cout=0, cin=0, cp=0):
+        nonlocal recs, n
+        off = 0
+        while off < cnt:
+            k = min(65536, cnt - off)
+            recs += struct.pack("<QQQQiiiiiiii", p + 4 * off, g + 4 * off, f, d, k, mode, off, cout, cin, cp, 0, 0)
+            off += k
+            n += 1
+    emit(w.data_ptr(), gw.data_ptr(), w.numel(), 2, wf.data_ptr(), wd.data_ptr(), 64, 13, 16)
+    emit(b.data_ptr(), gb.data_ptr(), b.numel(), 0)
+    emit(st.data_ptr(), st.data_ptr(), st.numel(), 1)
+    table = torch.frombuffer(recs, dtype=torch.uint8).clone().to(cuda)
+    _lib.check(_lib.load().fabric_b200_train_step_update(table.data_ptr(), n, 0.3, 0.5, 0.25, torch.cuda.current_stream().cuda_stream))
+    lr = torch.tensor(0.3, dtype=torch.float32) * torch.tensor(0.5, dtype=torch.float32)
+    assert torch.allclose(w, w0 - float(lr) * gw, rtol=0, atol=1e-6) and torch.allclose(b, b0 - float(lr) * gb, rtol=0, atol=1e-6)
+    assert torch.equal(st, st0 * 0.25)
+    assert torch.equal(wf, ops.pack_conv_weight(w, 0)) and torch.equal(wd, ops.pack_conv_weight(w, 1))

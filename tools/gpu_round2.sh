@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box call of round 2: parity tests, the default bench line (train + infer + library bar + cpu baseline), the
+# reference arm, sanitizer runs, ncu launch list of the training step.   usage: bash tools/gpu_round2.sh [tag] [what...]
+TAG=${1:-r02}
+shift
+WHAT=${@:-tests bench ref sanitize launches}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader
+for w in $WHAT; do case $w in
+tests)
+  echo "== pytest -m gpu"
+  timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $O/${TAG}_pytest_gpu.log ;;
+tests_all)
+  echo "== pytest -m gpu (no -x)"
+  timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -60 | tee $O/${TAG}_pytest_gpu.log ;;
+bench)
+  echo "== bench (default: train)"
+  timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err ;;
+ref)
+  echo "== reference arm"
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>/dev/null; tail -c 400 $O/${TAG}_bench_reference.json ;;
+sanitize)
+  bash tools/sanitize.sh $TAG ;;
+launches)
+  echo "== launch list (train step)"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_bench_train.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-library --no-scene --no-infer --e2e-steps 1 > $O/${TAG}_launches_train.log 2>&1
+  python tools/summarize_launches.py $O/${TAG}_launches_bench_train.csv > $O/${TAG}_launches_train_summary.md 2>&1; head -40 $O/${TAG}_launches_train_summary.md ;;
+smoke)
+  echo "== smoke"
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 ;;
+esac; done
+du -sh $O

@@ -8,8 +8,20 @@ from collections import OrderedDict
 rows = list(csv.reader(open(sys.argv[1])))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "ID") + 1
 L = [(r[4], int(r[-1])) for r in rows[start:] if len(r) > 10]
-first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-n = int(sys.argv[3]) if len(sys.argv) > 3 else len(L)
+if len(sys.argv) > 2 and not sys.argv[2].startswith("auto"):
+    first = int(sys.argv[2])
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else len(L)
+else:
+    # auto: one steady-state step = the launches between two consecutive occurrences of the step's LAST kernel
+    # (default: the fused optimizer update of a training step), taking the 4th such interval (after the warm-up steps)
+    marker = sys.argv[2].split(":", 1)[1] if len(sys.argv) > 2 and ":" in sys.argv[2] else "train_step_update"
+    idx = [i for i, (nm, _) in enumerate(L) if marker in nm]
+    if len(idx) >= 5:
+        first, n = idx[3] + 1, idx[4] - idx[3]
+    elif len(idx) >= 2:
+        first, n = idx[-2] + 1, idx[-1] - idx[-2]
+    else:
+        first, n = 0, len(L)
 step = L[first:first + n]
 tot = sum(t for _, t in step)
 agg = OrderedDict()
