@@ -333,6 +333,55 @@ def library_baseline(dev, steps=6, warm=3):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ launch-bound shapes
+def small_shape_record(dev, steps=30):
+    """BASELINE configs[0] (2 pairs 13x32x32) and the reference's default geometry (32 pairs 13x90x90, metadata.json:32-33,40):
+    the same training step, launch by launch (eager) and as ONE CUDA graph (fabric_b200.graph.GraphedTrainStep).  At these
+    sizes the step is bound by the host side of ~180 launches, not by the GPU."""
+    import torch
+    from fabric_b200 import BiDateNet
+    from fabric_b200.distributed import DataParallelStep
+    from fabric_b200.graph import GraphedTrainStep
+    from fabric_b200.metrics import TverskyLoss
+    out = {}
+    crit = TverskyLoss(alpha=0.1, beta=0.9)
+    for name, b, s_ in (("config1_2x13x32x32", 2, 32), ("reference_default_32x13x90x90", 32, 90)):
+        try:
+            torch.manual_seed(0)
+            model = BiDateNet(13, 2).to(dev).train()
+            dp = DataParallelStep(model)
+            g = torch.Generator(device=dev).manual_seed(3)
+            x1 = torch.randn(b, 13, s_, s_, device=dev, generator=g)
+            x2 = torch.randn(b, 13, s_, s_, device=dev, generator=g)
+            lab = (torch.rand(b, s_, s_, device=dev, generator=g) < 0.1).long()
+
+            def eager():
+                dp.zero_grad()
+                loss = crit(model(x1, x2), lab)
+                loss.backward()
+                dp.sync_and_step(LR)
+            graphed = GraphedTrainStep(model, crit, dp, LR, (x1, x2, lab))
+            rec = {}
+            for kind, fn in (("eager", eager), ("cuda_graph", lambda: graphed(x1, x2, lab))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()           # wall clock on purpose: the host is the bottleneck being measured
+                for _ in range(steps):
+                    fn()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / steps
+                rec[kind] = {"ms_per_step": dt * 1e3, "value": b / dt, "unit": "patch-pairs/s"}
+            rec["graph_speedup"] = rec["eager"]["ms_per_step"] / rec["cuda_graph"]["ms_per_step"]
+            out[name] = rec
+            dp.close()
+            del graphed, model, dp
+        except Exception as e:
+            out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def summarise_profile(prof, steps):
     """(total conv ms, total algorithmic flops, per-layer dict, per-kind dict) from ops.CONV_PROFILE records."""
@@ -385,6 +434,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library", action="store_true", help="skip the torch / cuDNN library bar")
     ap.add_argument("--no-scene", action="store_true", help="skip the scene sub-record of the default line")
+    ap.add_argument("--no-small", action="store_true", help="skip the launch-bound small-shape sub-record (eager vs CUDA graph)")
     ap.add_argument("--no-infer", action="store_true", help="skip the eval-forward sub-record of the train line")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunk", type=int, default=32, help="pairs per sub-batch of the host pipeline (infer e2e leg)")
@@ -657,6 +707,9 @@ def main():
             scene = scene_record(args, dev, rank, world, args.scene, steps=2, warm=1, e2e=False)
         except Exception as e:
             scene = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    small = None
+    if world == 1 and train and not args.no_small:
+        small = small_shape_record(dev)
     lib = None
     if rank == 0 and not args.no_library:
         lib = library_baseline(dev)
@@ -677,7 +730,7 @@ def main():
             "tflops_per_gpu": (TRAIN_GFLOP_PER_PAIR if train else FWD_GFLOP_PER_PAIR) * PAIRS / ms_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, **e2e_extra,
             "gpu_launches": launches, "numa_node": numa, "layers": layers, "infer": infer, "scene": scene,
-            "library_baseline": lib,
+            "launch_bound_shapes": small, "library_baseline": lib,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

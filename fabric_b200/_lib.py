@@ -74,11 +74,16 @@ SIGNATURES = {
     "fabric_b200_bn_apply_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_seg_loss_ws_floats": (_i64, [_i, _i, _i]),
     "fabric_b200_seg_loss_fwd_bwd": (_i, [_i, _f, _f, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "fabric_b200_seg_loss_sums_offset": (_i64, [_i, _i, _i]),
+    "fabric_b200_seg_loss_phase": (_i, [_i, _i, _f, _f, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp]),
     "fabric_b200_outconv_bwd_ws_floats": (_i64, [_i]),
     "fabric_b200_outconv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_bn_bwd_ws_floats": (_i64, [_i, _i]),
     "fabric_b200_bn_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_bwd_partial_floats": (_i64, [_i, _i]),
+    "fabric_b200_bn_relu_bwd_phase": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _i, _i, _i, _i, _i, _f, _f, _vp]),
     "fabric_b200_up_input_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_conv3x3_wgrad_plan": (_i, [C.POINTER(WgradDesc), _i, _i, C.POINTER(WgradPlan)]),
     "fabric_b200_conv3x3_wgrad_ws_floats": (_i64, [C.POINTER(WgradDesc)]),

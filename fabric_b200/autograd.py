@@ -73,7 +73,7 @@ class _BiDateNetTrain(torch.autograd.Function):
         dev = x5.device
 
         def cat(level, cs, cl):     # decoder input; the skip half (relu(d2*d1)) is written by the encoder's BN-apply kernel
-            return torch.empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
+            return ops._empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
         cat4, cat3, cat2, cat1 = cat(0, 64, 64), cat(1, 128, 128), cat(2, 256, 256), cat(3, 512, 512)
         sv = {}
         e1, p1, sv["inc"] = _dc_forward(model.inc.conv, x5, True, cat4)                 # bidate_model.py:23,29 (+:38 skip)

@@ -61,7 +61,7 @@ class BiDateNet(_CacheInvalidation, nn.Module):
         """Both dates into one NHWC5 bf16 tensor [2,B,H,W,16].  ``aug`` int32 [B,3] (rot90 turns, flip rows, flip columns)
         applies the loader's augmentation while packing (use ``ops.augment_labels`` with the same rows for the labels)."""
         b, c, h, w = x_d1.shape
-        x5 = torch.empty((2, b, h, w, ops.cpad(c)), dtype=torch.bfloat16, device=x_d1.device)
+        x5 = ops._empty((2, b, h, w, ops.cpad(c)), dtype=torch.bfloat16, device=x_d1.device)
         if aug is not None:
             mean, inv_std = getattr(self, "_fb_in_mean", None), getattr(self, "_fb_in_inv_std", None)
             if x_d1.dtype == torch.uint16 and mean is None:
@@ -90,7 +90,7 @@ class BiDateNet(_CacheInvalidation, nn.Module):
         dev = x5.device
 
         def cat(level, cs, cl):     # decoder input [1,B,H/2^l,W/2^l,cs+cl]; skip half filled by the encoder epilogue
-            return torch.empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
+            return ops._empty((1, b, h >> level, w >> level, cs + cl), dtype=torch.bfloat16, device=dev)
         cat4, cat3, cat2, cat1 = cat(0, 64, 64), cat(1, 128, 128), cat(2, 256, 256), cat(3, 512, 512)
         # the full-resolution encoder outputs are consumed only through their pooled copy and the fused product, so the
         # 64- and 128-wide levels do not write them at all (the date-0 tile waits in shared memory for its partner)

@@ -248,7 +248,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything arrives on them
-  else __syncthreads();
+  // (CTAS == 2: barrier.cluster already orders the allocator's shared-memory write of the TMEM address before the reads
+  //  below; compute-sanitizer's racecheck does not model it as a CTA barrier and reported that one pattern, 147 times,
+  //  as a hazard -- profiles/r02_sanitizer.md -- so the CTA barrier is executed as well: once per kernel, free)
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 

@@ -244,10 +244,10 @@ __global__ void seg_loss_grad_kernel(const float* __restrict__ logits, const lon
 
 // focal (gamma) / cross entropy (gamma = 0): loss partial sums + gradient in one pass (pt detached, metrics.py:35)
 __global__ void focal_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int H, int W,
-                                  float gamma, float* __restrict__ dlogits, float* __restrict__ partial) {
+                                  float gamma, float* __restrict__ dlogits, float* __restrict__ partial, float mean_scale) {
   __shared__ float red[32];
   const size_t plane = (size_t)H * W, total = (size_t)B * plane;
-  const float invn = 1.f / (float)total;
+  const float invn = mean_scale / (float)total;
   float acc = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / plane, o = i % plane;
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwd p, float* _
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int G, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        const float* __restrict__ mean, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef) {
+                                       float* __restrict__ dbeta, float* __restrict__ coef, float grad_scale) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -493,8 +493,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
     }
   }
   if (lane == 0) {
-    dgamma[c] = (float)dg;
-    dbeta[c] = (float)db;
+    dgamma[c] = (float)dg * grad_scale;
+    dbeta[c] = (float)db * grad_scale;
   }
 }
 
@@ -830,9 +830,12 @@ int64_t fabric_b200_seg_loss_ws_floats(int B, int H, int W) {
   return (int64_t)nblk * 6 * W + 10 * (int64_t)W + 1024;
 }
 
-int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma, float eps, const float* logits,
-                                 const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
-                                 float* ws, void* stream) {
+// phase bits: 1 = per-column sums [6][W] (I_c, P_c, T_c) into the workspace tail; 2 = loss + dL/dlogits from those sums.
+// Between the two a data-parallel caller may all-reduce the sums (exact-global loss, reference train.py:91-92 computes the
+// loss on the gathered batch).  Focal / CE are plain means: `mean_scale` (1/world) scales their loss and gradient instead.
+static int seg_loss_phases(int phase, int kind, float alpha, float beta, float gamma, float eps, const float* logits,
+                           const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
+                           float* ws, float mean_scale, void* stream) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
@@ -847,29 +850,56 @@ int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma,
     const int nblk = (rows + rpb - 1) / rpb;
     float* partial = ws;
     float* coef = ws + (size_t)nblk * 6 * W;
-    seg_loss_partial_kernel<<<nblk, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, H, W, rpb, partial);
-    FB_CUDA(cudaGetLastError());
-    const size_t smem = 6 * (size_t)W * sizeof(float);
-    FB_CUDA(cudaFuncSetAttribute(seg_loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float* sums = coef + 4 * (size_t)W;  // [6][W], inside the workspace tail
-    reduce_partials_kernel<<<(6 * W + 255) / 256, 256, 0, st>>>(partial, nblk, 6 * W, sums);
-    FB_CUDA(cudaGetLastError());
-    seg_loss_finalize_kernel<<<1, 256, smem, st>>>(sums, 1, W, label_ndim, kind, alpha, beta, eps, coef, loss_out);
-    FB_CUDA(cudaGetLastError());
-    seg_loss_grad_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), coef, B,
-                                                                H, W, dlogits);
-    FB_CUDA(cudaGetLastError());
-  } else if (kind == 3 || kind == 4) {  // focal / cross entropy
-    const int nblk = 296;
-    focal_loss_kernel<<<nblk, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, H, W,
-                                            kind == 4 ? 0.f : gamma, dlogits, ws);
-    FB_CUDA(cudaGetLastError());
-    reduce_partials_kernel<<<1, 32, 0, st>>>(ws, nblk, 1, loss_out);
-    FB_CUDA(cudaGetLastError());
+    if (phase & 1) {
+      seg_loss_partial_kernel<<<nblk, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, H, W, rpb, partial);
+      FB_CUDA(cudaGetLastError());
+      reduce_partials_kernel<<<(6 * W + 255) / 256, 256, 0, st>>>(partial, nblk, 6 * W, sums);
+      FB_CUDA(cudaGetLastError());
+    }
+    if (phase & 2) {
+      const size_t smem = 6 * (size_t)W * sizeof(float);
+      FB_CUDA(cudaFuncSetAttribute(seg_loss_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      seg_loss_finalize_kernel<<<1, 256, smem, st>>>(sums, 1, W, label_ndim, kind, alpha, beta, eps, coef, loss_out);
+      FB_CUDA(cudaGetLastError());
+      seg_loss_grad_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), coef, B,
+                                                                  H, W, dlogits);
+      FB_CUDA(cudaGetLastError());
+    }
+  } else if (kind == 3 || kind == 4) {  // focal / cross entropy: one pass, nothing to exchange (phase 1 is empty)
+    if (phase & 2) {
+      const int nblk = 296;
+      focal_loss_kernel<<<nblk, 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, H, W,
+                                              kind == 4 ? 0.f : gamma, dlogits, ws, mean_scale);
+      FB_CUDA(cudaGetLastError());
+      reduce_partials_kernel<<<1, 32, 0, st>>>(ws, nblk, 1, loss_out);
+      FB_CUDA(cudaGetLastError());
+    }
   } else {
     return fail(FB_ERR_ARG, "unknown loss kind %d", kind);
   }
   return FB_OK;
+}
+
+int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma, float eps, const float* logits,
+                                 const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
+                                 float* ws, void* stream) {
+  return seg_loss_phases(3, kind, alpha, beta, gamma, eps, logits, labels, label_ndim, B, H, W, loss_out, dlogits, ws, 1.f, stream);
+}
+
+int fabric_b200_seg_loss_phase(int phase, int kind, float alpha, float beta, float gamma, float eps, const float* logits,
+                               const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
+                               float* ws, float mean_scale, void* stream) {
+  if (phase != 1 && phase != 2) return fail(FB_ERR_ARG, "phase must be 1 (sums) or 2 (loss + gradient)");
+  return seg_loss_phases(phase, kind, alpha, beta, gamma, eps, logits, labels, label_ndim, B, H, W, loss_out, dlogits, ws,
+                         mean_scale, stream);
+}
+
+int64_t fabric_b200_seg_loss_sums_offset(int B, int H, int W) {
+  const int rows = B * H;
+  const int rpb = (rows + 295) / 296;
+  const int nblk = (rows + rpb - 1) / rpb;
+  return (int64_t)nblk * 6 * W + 4 * (int64_t)W;
 }
 
 int fabric_b200_outconv_bwd(const float* dlogits, const void* u, const float* w, void* du, float* dw, float* db, float* ws,
@@ -907,10 +937,13 @@ int64_t fabric_b200_bn_bwd_ws_floats(int G, int C) {
   return (int64_t)di.sms * 3 * G * C * 2 + (int64_t)G * 3 * C;
 }
 
-int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga_groups, int ga_channels, int mul_other,
-                            const void* gp, const float* scale, const float* shift, const float* mean, const float* invstd,
-                            const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws, int G, int B, int H, int W,
-                            int C, void* stream) {
+// phase bits: 1 = reduce pass (partials into ws), 2 = finalize + apply pass.  `count_scale` multiplies the per-group element
+// count (exact-global BatchNorm: world size, after the caller all-reduced the partials in ws); `grad_scale` multiplies
+// dgamma / dbeta (1/world there, so that the SUM all-reduce of the gradient bucket restores the global value).
+static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const void* ga, int ga_groups, int ga_channels,
+                              int mul_other, const void* gp, const float* scale, const float* shift, const float* mean,
+                              const float* invstd, const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws, int G,
+                              int B, int H, int W, int C, float count_scale, float grad_scale, void* stream) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
@@ -932,18 +965,47 @@ int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga
   float* coef = ws + (size_t)nblk * G * C * 2;
   // product-fused encoder levels: both date groups per thread (see bn_bwd2_dy)
   const bool dual = mul_other && G == 2 && ga && ga_groups == 1;
-  if (dual && gp) bn_bwd2_reduce_kernel<true><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
-  else if (dual) bn_bwd2_reduce_kernel<false><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
-  else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
-  FB_CUDA(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, G, C, (double)B * H * W, gamma, invstd, mean, dgamma, dbeta, coef);
-  FB_CUDA(cudaGetLastError());
-  const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
-  if (dual && gp) bn_bwd2_apply_kernel<true><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
-  else if (dual) bn_bwd2_apply_kernel<false><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
-  else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
-  FB_CUDA(cudaGetLastError());
+  if (phase & 1) {
+    if (dual && gp) bn_bwd2_reduce_kernel<true><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+    else if (dual) bn_bwd2_reduce_kernel<false><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+    else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+    FB_CUDA(cudaGetLastError());
+  }
+  if (phase & 2) {
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, G, C, (double)B * H * W * (double)count_scale, gamma, invstd,
+                                                        mean, dgamma, dbeta, coef, grad_scale);
+    FB_CUDA(cudaGetLastError());
+    const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
+    if (dual && gp) bn_bwd2_apply_kernel<true><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+    else if (dual) bn_bwd2_apply_kernel<false><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+    else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+    FB_CUDA(cudaGetLastError());
+  }
   return FB_OK;
+}
+
+int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga_groups, int ga_channels, int mul_other,
+                            const void* gp, const float* scale, const float* shift, const float* mean, const float* invstd,
+                            const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws, int G, int B, int H, int W,
+                            int C, void* stream) {
+  return bn_relu_bwd_phases(3, z, a, ga, ga_groups, ga_channels, mul_other, gp, scale, shift, mean, invstd, gamma, dz, dgamma,
+                            dbeta, ws, G, B, H, W, C, 1.f, 1.f, stream);
+}
+
+int fabric_b200_bn_relu_bwd_phase(int phase, const void* z, const void* a, const void* ga, int ga_groups, int ga_channels,
+                                  int mul_other, const void* gp, const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws,
+                                  int G, int B, int H, int W, int C, float count_scale, float grad_scale, void* stream) {
+  if (phase != 1 && phase != 2) return fail(FB_ERR_ARG, "phase must be 1 (reduce) or 2 (finalize + apply)");
+  return bn_relu_bwd_phases(phase, z, a, ga, ga_groups, ga_channels, mul_other, gp, scale, shift, mean, invstd, gamma, dz,
+                            dgamma, dbeta, ws, G, B, H, W, C, count_scale, grad_scale, stream);
+}
+
+int64_t fabric_b200_bn_bwd_partial_floats(int G, int C) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  return (int64_t)di.sms * 2 * G * C * 2;
 }
 
 int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream) {

@@ -36,9 +36,15 @@ def _block_of(name: str) -> str:
 
 
 class DataParallelStep:
-    def __init__(self, model, process_group=None, overlap: bool = True, manage_packed: bool = True):
+    def __init__(self, model, process_group=None, overlap: bool = True, manage_packed: bool = True, exact: bool = False):
         self.model = model
         self.pg = process_group
+        # exact-global mode: SyncBN + loss on the global batch; gradients are then SUMMED (each rank holds its share of the
+        # global gradient), BatchNorm affine gradients arrive pre-divided by world (see ops.bn_relu_bwd)
+        self.exact = bool(exact)
+        if self.exact:
+            from . import ops
+            ops.EXACT = ops.ExactGlobal(process_group)
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         # backward order for BiDateNet (so that finished gradients form a growing prefix of the bucket)
         try:
@@ -161,7 +167,10 @@ class DataParallelStep:
         if self.world == 1:
             return
         self._reduce()
-        self.bucket.mul_(1.0 / self.world)
+        if self.exact:
+            self.bucket[self.n_grad:].mul_(1.0 / self.world)     # gradients are already the global ones; statistics: mean
+        else:
+            self.bucket.mul_(1.0 / self.world)
 
     # ------------------------------------------------------------------------------------------------ fused step
     def _manage_packed(self):
@@ -171,18 +180,23 @@ class DataParallelStep:
         from . import ops
         from .unet_parts import double_conv
         self._packed = {}
+        fresh = False
         for m in self.model.modules():
             if isinstance(m, double_conv):
+                old = m.__dict__.get("_fb_managed") or {}
+                fresh = fresh or not old
                 managed = {}
                 for idx in (0, 3):
                     w = m.conv[idx].weight
-                    managed[("w", idx)] = ops.pack_conv_weight(w, 0)
-                    managed[("wd", idx)] = ops.pack_conv_weight(w, 1)
+                    # refresh IN PLACE when the copies exist: a captured CUDA graph has their addresses baked in
+                    managed[("w", idx)] = ops.pack_conv_weight(w, 0, out=old.get(("w", idx)))
+                    managed[("wd", idx)] = ops.pack_conv_weight(w, 1, out=old.get(("wd", idx)))
                     managed[("v", idx)] = w._version
                     self._packed[w] = (managed[("w", idx)], managed[("wd", idx)])
                 m.__dict__["_fb_managed"] = managed
         self._managed = True
-        self._table = None
+        if fresh:
+            self._table = None          # new buffers: the update kernel's record table must be rebuilt
 
     def _update_table(self):
         """device table of 64-byte records for fabric_b200_train_step_update (<= 64 Ki elements each), built once"""
@@ -227,10 +241,17 @@ class DataParallelStep:
         table, n_sgd, n_all = self._update_table()
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().fabric_b200_train_step_update(
-                table.data_ptr(), n_all if world > 1 else n_sgd, float(lr), 1.0 / world, 1.0 / world,
+                table.data_ptr(), n_all if world > 1 else n_sgd, float(lr), 1.0 if self.exact else 1.0 / world, 1.0 / world,
                 torch.cuda.current_stream().cuda_stream), "train_step_update")
         ops._count()
         self.invalidate()
+
+    def close(self):
+        """detach from the model (and leave exact-global mode)"""
+        from . import ops
+        if self.exact:
+            ops.EXACT = None
+        self.model.__dict__.pop("_fb_dp", None)
 
     def invalidate(self):
         """the kernel updated the parameters behind torch's back (no version bump): drop version-keyed caches"""

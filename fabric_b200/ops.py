@@ -6,6 +6,7 @@ run through the weight-shared encoder as one launch, 1 in the decoder).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -18,6 +19,54 @@ from ._lib import Conv3x3Desc, ConvTuning, check
 # every conv launch on the launching stream so the roofline figure is measured live inside the timed region
 LAUNCHES = 0
 CONV_PROFILE = None   # set to a list to collect (tag, start_event, end_event, algorithmic_flops)
+
+
+# FABRIC_B200_POISON=1: every output / workspace tensor allocated here starts as NaN (floats) or 0xFF bytes (integers)
+# instead of whatever the caching allocator hands back, so a kernel that READS anything it (or its producer) did not write
+# turns a test red instead of passing by luck.  The GPU test-suite is run once in this mode (tools/gpu_round2.sh poison):
+# it is the initcheck that also covers tensors written by TMA stores, which compute-sanitizer's initcheck cannot see.
+POISON = os.environ.get("FABRIC_B200_POISON", "0") == "1"
+
+
+class ExactGlobal:
+    """Exact-global data-parallel arithmetic: while ``ops.EXACT`` holds one of these, BatchNorm batch
+    statistics (forward moments and the backward (sum dy, sum dy*xhat) pairs) and the loss sums are all-reduced across the
+    process group between the kernels' reduce and finalize phases, so that N ranks x B pairs compute what one rank would
+    compute on N*B pairs (SyncBN == the reference's single-device statistics; loss on the gathered batch, train.py:91-92).
+    Latency-bound collectives on the critical path: off by default (``DataParallelStep(exact=True)`` turns it on)."""
+
+    def __init__(self, process_group=None):
+        import torch.distributed as dist
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.collectives = 0
+
+    def all_reduce(self, t: torch.Tensor):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+            self.collectives += 1
+        return t
+
+
+EXACT: Optional[ExactGlobal] = None
+
+
+def _poison(t: torch.Tensor) -> torch.Tensor:
+    if POISON and t.numel():
+        if t.dtype.is_floating_point:
+            t.fill_(float("nan"))
+        else:
+            t.view(torch.uint8).fill_(0xFF)
+    return t
+
+
+def _empty(*a, **kw) -> torch.Tensor:
+    return _poison(torch.empty(*a, **kw))
+
+
+def _empty_like(t: torch.Tensor) -> torch.Tensor:
+    return _poison(torch.empty_like(t))
 
 
 def _count(n: int = 1):
@@ -68,7 +117,7 @@ def pack_input(x: torch.Tensor, out: Optional[torch.Tensor] = None, c_pad: Optio
     b, c, h, w = x.shape
     c_pad = c_pad or cpad(c)
     if out is None:
-        out = torch.empty((b, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+        out = _empty((b, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
     assert out.shape == (b, h, w, c_pad) and out.dtype == torch.bfloat16
     check(_lib.load().fabric_b200_pack_nchw_f32_to_nhwc_bf16(_p(x), _p(out), b, c, c_pad, h, w, _stream()), "pack_input")
     _count()
@@ -84,7 +133,7 @@ def pack_input_raw(x: torch.Tensor, mean: torch.Tensor, inv_std: torch.Tensor, o
     b, c, h, w = x.shape
     assert mean.dtype == torch.float32 and inv_std.dtype == torch.float32 and mean.numel() == c and inv_std.numel() == c
     if out is None:
-        out = torch.empty((b, h, w, 16), dtype=torch.bfloat16, device=x.device)
+        out = _empty((b, h, w, 16), dtype=torch.bfloat16, device=x.device)
     assert out.shape == (b, h, w, 16) and out.dtype == torch.bfloat16
     check(_lib.load().fabric_b200_pack_nchw_u16_to_nhwc_bf16(_p(x), _p(out), _p(mean), _p(inv_std), b, c, h, w, _stream()),
           "pack_input_raw")
@@ -100,7 +149,7 @@ def pack_input_aug(x: torch.Tensor, aug: torch.Tensor, mean=None, inv_std=None, 
     assert s == s2 and aug.dtype == torch.int32 and aug.shape == (b, 3)
     dt = {torch.float32: 0, torch.uint16: 1}[x.dtype]
     if out is None:
-        out = torch.empty((b, s, s, 16), dtype=torch.bfloat16, device=x.device)
+        out = _empty((b, s, s, 16), dtype=torch.bfloat16, device=x.device)
     check(_lib.load().fabric_b200_pack_nchw_aug(_p(x), dt, _p(out), _p(aug), _p(mean), _p(inv_std), b, c, s, _stream()),
           "pack_input_aug")
     _count()
@@ -112,7 +161,7 @@ def augment_labels(labels: torch.Tensor, aug: torch.Tensor) -> torch.Tensor:
     _need_cuda(labels, aug)
     b, s, s2 = labels.shape
     assert s == s2 and labels.dtype == torch.int64 and aug.dtype == torch.int32 and aug.shape == (b, 3)
-    out = torch.empty_like(labels)
+    out = _empty_like(labels)
     check(_lib.load().fabric_b200_augment_labels(_p(labels), _p(out), _p(aug), b, s, _stream()), "augment_labels")
     _count()
     return out
@@ -122,13 +171,14 @@ def unpack_output(x: torch.Tensor) -> torch.Tensor:
     """NHWC bf16 [B,H,W,C] -> NCHW fp32 [B,C,H,W]."""
     _need_cuda(x)
     b, h, w, c = x.shape
-    out = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device)
+    out = _empty((b, c, h, w), dtype=torch.float32, device=x.device)
     check(_lib.load().fabric_b200_unpack_nhwc_bf16_to_nchw_f32(_p(x), _p(out), b, c, h, w, _stream()), "unpack_output")
     _count()
     return out
 
 
-def pack_conv_weight(w: torch.Tensor, mode: int = 0, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, mode: int = 0, scale: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[Cout,Cin,3,3] fp32 -> bf16 [Cout,9,CinPad] (mode 0, forward) or [Cin,9,Cout] with flipped taps (mode 1, dgrad).
     ``scale`` [Cout] fp32 (mode 0 only) multiplies each output channel's filter before rounding: the eval-mode BatchNorm
     scale folded into the weights (see ``conv3x3(..., shift_in_acc=True)``)."""
@@ -137,12 +187,11 @@ def pack_conv_weight(w: torch.Tensor, mode: int = 0, scale: Optional[torch.Tenso
     if w.dtype != torch.float32:
         w = w.float()
     cout, cin = w.shape[0], w.shape[1]
-    if mode == 0:
-        cp = cpad(cin)
-        out = torch.empty((cout, 9, cp), dtype=torch.bfloat16, device=w.device)
-    else:
-        cp = cin
-        out = torch.empty((cin, 9, cout), dtype=torch.bfloat16, device=w.device)
+    cp = cpad(cin) if mode == 0 else cin
+    shape = (cout, 9, cp) if mode == 0 else (cin, 9, cout)
+    if out is None:
+        out = _empty(shape, dtype=torch.bfloat16, device=w.device)
+    assert out.shape == shape and out.dtype == torch.bfloat16 and out.is_contiguous()
     check(_lib.load().fabric_b200_pack_conv3x3_weight_scaled(_p(w), _p(scale), _p(out), cout, cin, cp, mode, _stream()),
           "pack_conv_weight")
     _count()
@@ -153,8 +202,8 @@ def bn_fold_eval(bn: torch.nn.BatchNorm2d, conv_bias: Optional[torch.Tensor]):
     """Eval-mode BatchNorm + conv bias as per-channel (scale, shift) for the conv epilogue."""
     c = bn.num_features
     dev = bn.weight.device
-    scale = torch.empty(c, dtype=torch.float32, device=dev)
-    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = _empty(c, dtype=torch.float32, device=dev)
+    shift = _empty(c, dtype=torch.float32, device=dev)
     check(_lib.load().fabric_b200_bn_fold_eval(_p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean),
                                                _p(bn.running_var), _p(None if conv_bias is None else conv_bias.detach()),
                                                float(bn.eps), _p(scale), _p(shift), c, _stream()), "bn_fold_eval")
@@ -193,17 +242,17 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
     res = {}
     y = None
     if store_main:
-        y = out if out is not None else torch.empty((g, b, h, w, cout), dtype=torch.bfloat16, device=x5.device)
+        y = out if out is not None else _empty((g, b, h, w, cout), dtype=torch.bfloat16, device=x5.device)
         assert y.shape == (g, b, h, w, cout)
     res["y"] = y
     d.x, d.w, d.y = _p(x5), _p(w_packed), _p(y)
     d.scale, d.shift = _p(scale), _p(shift)
     if pool:
-        res["pool"] = torch.empty((g, b, h // 2, w // 2, cout), dtype=torch.bfloat16, device=x5.device)
+        res["pool"] = _empty((g, b, h // 2, w // 2, cout), dtype=torch.bfloat16, device=x5.device)
         d.pool_out = _p(res["pool"])
     if head is not None:
         hw, hb = head
-        res["logits"] = torch.empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
+        res["logits"] = _empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
         d.head_w, d.head_b, d.head_out = _p(hw), _p(hb), _p(res["logits"])
     if prod_out is not None:
         # fused relu(y[date 1] * y[date 0]) into channels [0, cout) of the decoder input [1,B,H,W,Ct]
@@ -213,7 +262,7 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
         # the workspace size depends on the grid the planner picks; the planner ignores the pointer value
         d.stats_ws = 1
         n = check(lib.fabric_b200_conv3x3_stats_ws_floats(C.byref(d)), "conv3x3 plan")
-        ws = torch.empty(n, dtype=torch.float32, device=x5.device)
+        ws = _empty(n, dtype=torch.float32, device=x5.device)
         d.stats_ws = _p(ws)
         grid = check(lib.fabric_b200_conv3x3_grid(C.byref(d)), "conv3x3 plan")
         res["stats"] = ws.view(grid, 2, -1, 2)
@@ -242,7 +291,7 @@ def build_up_input(skip5: Optional[torch.Tensor], low5: torch.Tensor, out: Optio
     if skip5 is not None:
         assert skip5.shape[0] == 2 and skip5.shape[1] == b
         _, _, h_, w_, cs = skip5.shape
-        out = torch.empty((1, b, h_, w_, cs + cl), dtype=torch.bfloat16, device=low5.device)
+        out = _empty((1, b, h_, w_, cs + cl), dtype=torch.bfloat16, device=low5.device)
     else:
         assert out is not None and out.shape[1] == b
         _, _, h_, w_, ct = out.shape
@@ -258,7 +307,7 @@ def outconv(x5: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
     _need_cuda(x5, weight, bias)
     g, b, h, w, c = x5.shape
     assert weight.shape[0] == 2, "the fused head is built for n_classes == 2"
-    out = torch.empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
+    out = _empty((g * b, 2, h, w), dtype=torch.float32, device=x5.device)
     check(_lib.load().fabric_b200_outconv(_p(x5), _p(weight.detach().reshape(2, c).contiguous()), _p(bias.detach()), _p(out),
                                           g * b, h, w, c, _stream()), "outconv")
     _count()
@@ -277,8 +326,13 @@ def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_
     grid, _, n_tile, _ = stats.shape
     c = bn.num_features
     dev = stats.device
-    out = [torch.empty((groups, c), dtype=torch.float32, device=dev) for _ in range(4)]
+    out = [_empty((groups, c), dtype=torch.float32, device=dev) for _ in range(4)]
     mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    if EXACT is not None and EXACT.world > 1:
+        # every rank launched the same grid: the element-wise SUM of the per-CTA partial arrays is a valid partial array of
+        # the global batch (finalize sums over CTAs), with world x the elements per group
+        EXACT.all_reduce(stats)
+        count_per_group = int(count_per_group) * EXACT.world
     check(_lib.load().fabric_b200_bn_finalize(_p(stats), grid, n_tile, c, groups, int(count_per_group),
                                               _p(None if conv_bias is None else conv_bias.detach()), _p(bn.weight.detach()),
                                               _p(bn.bias.detach()), _p(bn.running_mean), _p(bn.running_var),
@@ -295,8 +349,8 @@ def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, po
     """a = relu(z*scale[g]+shift[g]) (+ MaxPool2d(2) copy) (+ relu(a[1]*a[0]) into prod_out[..., :C], the skip half of the
     decoder input [1,B,H,W,Ct])."""
     g, b, h, w, c = z5.shape
-    a = torch.empty_like(z5)
-    pl = torch.empty((g, b, h // 2, w // 2, c), dtype=torch.bfloat16, device=z5.device) if pool else None
+    a = _empty_like(z5)
+    pl = _empty((g, b, h // 2, w // 2, c), dtype=torch.bfloat16, device=z5.device) if pool else None
     pc = 0
     if prod_out is not None:
         assert g == 2 and prod_out.shape[:4] == (1, b, h, w)
@@ -322,9 +376,22 @@ def seg_loss_fwd_bwd(kind: str, logits: torch.Tensor, labels: torch.Tensor, alph
         nd = 3 if nd not in (3, 4) else nd
     assert labels.numel() == b * h * w
     lib = _lib.load()
-    ws = torch.empty(check(lib.fabric_b200_seg_loss_ws_floats(b, h, w), "seg_loss ws"), dtype=torch.float32, device=logits.device)
-    loss = torch.empty((), dtype=torch.float32, device=logits.device)
-    dlogits = torch.empty_like(logits)
+    ws = _empty(check(lib.fabric_b200_seg_loss_ws_floats(b, h, w), "seg_loss ws"), dtype=torch.float32, device=logits.device)
+    loss = _empty((), dtype=torch.float32, device=logits.device)
+    dlogits = _empty_like(logits)
+    if EXACT is not None and EXACT.world > 1:
+        # loss on the global batch: sums all-reduced between the two phases (ratio losses), mean scaled by 1/world (focal / CE)
+        args = (LOSS_KINDS[kind], float(alpha), float(beta), float(gamma), float(eps), _p(logits), _p(labels), nd, b, h, w,
+                _p(loss), _p(dlogits), _p(ws), 1.0 / EXACT.world, _stream())
+        check(lib.fabric_b200_seg_loss_phase(1, *args), "seg_loss sums")
+        if LOSS_KINDS[kind] <= 2:
+            off = check(lib.fabric_b200_seg_loss_sums_offset(b, h, w), "seg_loss ws")
+            EXACT.all_reduce(ws[off:off + 6 * w])
+        check(lib.fabric_b200_seg_loss_phase(2, *args), "seg_loss")
+        if LOSS_KINDS[kind] > 2:
+            EXACT.all_reduce(loss)
+        _count(3)
+        return loss, dlogits
     check(lib.fabric_b200_seg_loss_fwd_bwd(LOSS_KINDS[kind], float(alpha), float(beta), float(gamma), float(eps), _p(logits),
                                            _p(labels), nd, b, h, w, _p(loss), _p(dlogits), _p(ws), _stream()), "seg_loss")
     _count(3)
@@ -337,10 +404,10 @@ def outconv_bwd(dlogits: torch.Tensor, u5: torch.Tensor, weight: torch.Tensor, d
     g, b, h, w, c = u5.shape
     lib = _lib.load()
     _need_cuda(dlogits, u5, dw_out, db_out)
-    ws = torch.empty(check(lib.fabric_b200_outconv_bwd_ws_floats(c), "outconv_bwd ws"), dtype=torch.float32, device=u5.device)
-    du = torch.empty_like(u5)
-    dw = dw_out if dw_out is not None else torch.empty((2, c), dtype=torch.float32, device=u5.device)
-    db = db_out if db_out is not None else torch.empty((2,), dtype=torch.float32, device=u5.device)
+    ws = _empty(check(lib.fabric_b200_outconv_bwd_ws_floats(c), "outconv_bwd ws"), dtype=torch.float32, device=u5.device)
+    du = _empty_like(u5)
+    dw = dw_out if dw_out is not None else _empty((2, c), dtype=torch.float32, device=u5.device)
+    db = db_out if db_out is not None else _empty((2,), dtype=torch.float32, device=u5.device)
     check(lib.fabric_b200_outconv_bwd(_p(dlogits), _p(u5), _p(weight.detach().reshape(2, c).contiguous()), _p(du), _p(dw),
                                       _p(db), _p(ws), g * b, h, w, c, _stream()), "outconv_bwd")
     _count(2)
@@ -353,11 +420,20 @@ def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma, dg
     g, b, h, w, c = z5.shape
     lib = _lib.load()
     _need_cuda(z5, a5, ga, gp, dgamma_out, dbeta_out)
-    ws = torch.empty(check(lib.fabric_b200_bn_bwd_ws_floats(g, c), "bn_bwd ws"), dtype=torch.float32, device=z5.device)
-    dz = torch.empty_like(z5)
-    dgamma = dgamma_out if dgamma_out is not None else torch.empty(c, dtype=torch.float32, device=z5.device)
-    dbeta = dbeta_out if dbeta_out is not None else torch.empty(c, dtype=torch.float32, device=z5.device)
+    ws = _empty(check(lib.fabric_b200_bn_bwd_ws_floats(g, c), "bn_bwd ws"), dtype=torch.float32, device=z5.device)
+    dz = _empty_like(z5)
+    dgamma = dgamma_out if dgamma_out is not None else _empty(c, dtype=torch.float32, device=z5.device)
+    dbeta = dbeta_out if dbeta_out is not None else _empty(c, dtype=torch.float32, device=z5.device)
     ga_groups, ga_ch = (ga.shape[0], ga.shape[4]) if ga is not None else (1, c)
+    if EXACT is not None and EXACT.world > 1:
+        args = (_p(z5), _p(a5), _p(ga), ga_groups, ga_ch, int(mul_other), _p(gp), _p(scale), _p(shift), _p(mean), _p(invstd),
+                _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws), g, b, h, w, c, float(EXACT.world), 1.0 / EXACT.world,
+                _stream())
+        check(lib.fabric_b200_bn_relu_bwd_phase(1, *args), "bn_relu_bwd reduce")
+        EXACT.all_reduce(ws[:check(lib.fabric_b200_bn_bwd_partial_floats(g, c), "bn_bwd ws")])
+        check(lib.fabric_b200_bn_relu_bwd_phase(2, *args), "bn_relu_bwd apply")
+        _count(3)
+        return dz, dgamma, dbeta
     check(lib.fabric_b200_bn_relu_bwd(_p(z5), _p(a5), _p(ga), ga_groups, ga_ch, int(mul_other), _p(gp), _p(scale), _p(shift),
                                       _p(mean), _p(invstd), _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws),
                                       g, b, h, w, c, _stream()), "bn_relu_bwd")
@@ -368,7 +444,7 @@ def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma, dg
 def up_input_bwd(dcat5: torch.Tensor, cs: int, h: int, w: int) -> torch.Tensor:
     _, b, hh, ww, ct = dcat5.shape
     cl = ct - cs
-    dlow = torch.empty((1, b, h, w, cl), dtype=torch.bfloat16, device=dcat5.device)
+    dlow = _empty((1, b, h, w, cl), dtype=torch.bfloat16, device=dcat5.device)
     check(_lib.load().fabric_b200_up_input_bwd(_p(dcat5), _p(dlow), b, hh, ww, cs, h, w, cl, _stream()), "up_input_bwd")
     _count()
     return dlow
@@ -390,7 +466,7 @@ def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: in
     d.ws = 16  # planner only checks alignment/non-null later
     n = check(lib.fabric_b200_conv3x3_wgrad_ws_floats(C.byref(d)), "wgrad plan")
     s = check(lib.fabric_b200_conv3x3_wgrad_splits(C.byref(d)), "wgrad plan")
-    ws = torch.empty(n, dtype=torch.float32, device=dz5.device)
+    ws = _empty(n, dtype=torch.float32, device=dz5.device)
     d.ws = _p(ws)
     prof = CONV_PROFILE
     if prof is not None:
@@ -400,7 +476,7 @@ def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: in
     if prof is not None:
         e1.record()
         prof.append((f"wgrad {cin_true}->{ca}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * ca))
-    dw = out if out is not None else torch.empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
+    dw = out if out is not None else _empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
     assert dw.shape == (ca, cin_true, 3, 3) and dw.dtype == torch.float32
     check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
     _count(2)
@@ -420,7 +496,7 @@ def gather_tiles(scene: torch.Tensor, origins: torch.Tensor, p: int, mean=None, 
         raise _lib.FabricB200Error("scene must be float32 or uint16")
     assert origins.dtype == torch.int32
     if out is None:
-        out = torch.empty((n, p, p, c_pad), dtype=torch.bfloat16, device=scene.device)
+        out = _empty((n, p, p, c_pad), dtype=torch.bfloat16, device=scene.device)
     check(_lib.load().fabric_b200_gather_tiles(_p(scene), dt, _p(origins), _p(out), _p(mean), _p(inv_std), n, c, c_pad, h, w, p,
                                                _stream()), "gather_tiles")
     _count()
@@ -437,7 +513,7 @@ def argmax_metrics(logits: torch.Tensor, labels: Optional[torch.Tensor] = None, 
         assert mask_out.shape == (b, h, w) and mask_out.dtype == torch.uint8
         mask = mask_out
     else:
-        mask = torch.empty((b, h, w), dtype=torch.uint8, device=logits.device) if want_mask else None
+        mask = _empty((b, h, w), dtype=torch.uint8, device=logits.device) if want_mask else None
     if labels is not None:
         if counts is None:
             counts = torch.zeros(4, dtype=torch.int64, device=logits.device)

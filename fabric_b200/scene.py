@@ -127,13 +127,13 @@ def predict_scene_band(model, band_d1: torch.Tensor, band_d2: torch.Tensor, plan
         origins = torch.tensor(plan.origins_list, dtype=torch.int32, device=dev)
         inv_std = (1.0 / std).float().contiguous() if std is not None else None
         mean = mean.float().contiguous() if mean is not None else None
-        masks = torch.empty((n, p, p), dtype=torch.uint8, device=dev)
-        x5 = torch.empty((2, min(batch_size, n), p, p, ops.cpad(c)), dtype=torch.bfloat16, device=dev)
+        masks = ops._empty((n, p, p), dtype=torch.uint8, device=dev)
+        x5 = ops._empty((2, min(batch_size, n), p, p, ops.cpad(c)), dtype=torch.bfloat16, device=dev)
         was_training = model.training
         model.eval()
         for s in range(0, n, batch_size):
             k = min(batch_size, n - s)
-            buf = x5[:, :k] if k == x5.shape[1] else torch.empty((2, k, p, p, ops.cpad(c)), dtype=torch.bfloat16, device=dev)
+            buf = x5[:, :k] if k == x5.shape[1] else ops._empty((2, k, p, p, ops.cpad(c)), dtype=torch.bfloat16, device=dev)
             ops.gather_tiles(band_d1, origins[s:s + k], p, mean, inv_std, out=buf[0])
             ops.gather_tiles(band_d2, origins[s:s + k], p, mean, inv_std, out=buf[1])
             logits = model.forward_packed(buf)

@@ -169,6 +169,16 @@ int fabric_b200_seg_loss_fwd_bwd(int kind, float alpha, float beta, float gamma,
                                  const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
                                  float* ws, void* stream);
 
+/* The same in two phases, for the exact-global loss of a data-parallel job (the reference computes the loss on the batch
+ * nn.DataParallel gathered, train.py:91-92; tversky / dice / jaccard are ratios of batch sums, so per-rank losses do not
+ * add up): phase 1 writes the per-column sums [6][W] (I_c, P_c, T_c for c = 0, 1) at ws + fabric_b200_seg_loss_sums_offset();
+ * the caller all-reduces those 6*W floats; phase 2 turns them into the loss and dL/dlogits.  Focal / CE are plain means:
+ * phase 1 does nothing and `mean_scale` (1/world) scales their loss and gradient in phase 2. */
+int64_t fabric_b200_seg_loss_sums_offset(int B, int H, int W);
+int fabric_b200_seg_loss_phase(int phase, int kind, float alpha, float beta, float gamma, float eps, const float* logits,
+                               const int64_t* labels, int label_ndim, int B, int H, int W, float* loss_out, float* dlogits,
+                               float* ws, float mean_scale, void* stream);
+
 /* ---- training: backward ----------------------------------------------------------------------------------------- */
 
 /* outconv backward: du = dlogits^T W (bf16 NHWC), dw [2][C], db [2] */
@@ -187,6 +197,16 @@ int fabric_b200_bn_relu_bwd(const void* z, const void* a, const void* ga, int ga
                             const void* gp, const float* scale, const float* shift, const float* mean, const float* invstd,
                             const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws, int G, int B, int H, int W,
                             int C, void* stream);
+
+/* The same in two phases, for exact-global BatchNorm (SyncBN == the reference's single-device statistics over the whole
+ * batch): phase 1 writes the (sum dy, sum dy*xhat) partials into the first fabric_b200_bn_bwd_partial_floats() floats of ws;
+ * the caller all-reduces them; phase 2 finishes with the element count multiplied by `count_scale` (world size) and
+ * dgamma / dbeta multiplied by `grad_scale` (1/world: the later SUM all-reduce of the gradients restores the global value). */
+int64_t fabric_b200_bn_bwd_partial_floats(int G, int C);
+int fabric_b200_bn_relu_bwd_phase(int phase, const void* z, const void* a, const void* ga, int ga_groups, int ga_channels,
+                                  int mul_other, const void* gp, const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws,
+                                  int G, int B, int H, int W, int C, float count_scale, float grad_scale, void* stream);
 
 /* adjoint of the upsample half of fabric_b200_build_up_input: dcat [B][H][W][Cs+Cl] -> dlow [B][h][w][Cl] */
 int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream);
