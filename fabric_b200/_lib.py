@@ -33,12 +33,14 @@ class Conv3x3Desc(C.Structure):
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
         ("prod_out", C.c_void_p), ("prod_channels", C.c_int), ("shift_in_acc", C.c_int),
         ("tune", ConvTuning),
+        ("bnbwd_z", C.c_void_p), ("bnbwd_coef", C.c_void_p),
     ]
 
 
 class ConvPlan(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_tile", "ck", "halo", "grid", "smem_bytes", "ctas", "epi_warps", "a_stages",
-                                       "b_stages", "b_resident", "out_bufs", "total_units", "pool_tma", "prod_tma", "ctas_per_sm")]
+                                       "b_stages", "b_resident", "out_bufs", "total_units", "pool_tma", "prod_tma", "ctas_per_sm",
+                                       "reg_stats")]
 
 
 class WgradDesc(C.Structure):
@@ -82,6 +84,8 @@ SIGNATURES = {
     "fabric_b200_bn_relu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_bn_bwd_partial_floats": (_i64, [_i, _i]),
+    "fabric_b200_bn_bwd_from_partials": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
+                                              _f, _f, _vp]),
     "fabric_b200_bn_relu_bwd_phase": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _i, _i, _i, _i, _i, _f, _f, _vp]),
     "fabric_b200_up_input_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -19,6 +19,10 @@ from . import ops
 
 KEEP_SAVED = False   # tests: keep the stored forward tensors of the last training forward in LAST_SAVED
 LAST_SAVED = None
+# the data-gradient conv of c2 masks its output with the ReLU of BatchNorm 1 and reduces (sum dy, sum dy*xhat) in its
+# epilogue, so BatchNorm 1's backward is ONE pass over (dy, z) instead of a reduce pass + an apply pass (False = the
+# stand-alone kernels, kept as the cross-check)
+FUSE_BN_BWD_REDUCE = True
 
 # backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
 BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")
@@ -52,11 +56,18 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None):
     # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
     grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
     grads[b2.weight], grads[b2.bias] = dg2, db2
-    da1 = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad")["y"]
-    del dz2
-    dz1, dg1, db1 = ops.bn_relu_bwd(sv["z1"], None, da1, False, None, *sv["s1"], b1.weight,
-                                    dgamma_out=sink.get(b1.weight), dbeta_out=sink.get(b1.bias))
-    del da1
+    if FUSE_BN_BWD_REDUCE:
+        r = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad", bnbwd=(sv["z1"], sv["s1"]))
+        del dz2
+        dz1, dg1, db1 = ops.bn_bwd_from_partials(sv["z1"], r["y"], r["stats"], sv["s1"], b1.weight,
+                                                 dgamma_out=sink.get(b1.weight), dbeta_out=sink.get(b1.bias))
+        del r
+    else:
+        da1 = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad")["y"]
+        del dz2
+        dz1, dg1, db1 = ops.bn_relu_bwd(sv["z1"], None, da1, False, None, *sv["s1"], b1.weight,
+                                        dgamma_out=sink.get(b1.weight), dbeta_out=sink.get(b1.bias))
+        del da1
     grads[c1.weight] = ops.conv3x3_wgrad(dz1, sv["x"], dc.in_ch, out=sink.get(c1.weight))
     grads[c1.bias] = sink[c1.bias] if c1.bias in sink else torch.zeros_like(c1.bias)
     grads[b1.weight], grads[b1.bias] = dg1, db1

@@ -10,6 +10,7 @@ namespace {
 struct ConvPlan {
   fb::Conv3x3Params p;
   int n_tile, ck, halo, grid, smem, ctas, ew, minb;
+  int rs;   // register-statistics instantiation (training launches of tiles with <= 2 chunks per epilogue warp)
 };
 
 int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di);
@@ -98,6 +99,12 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   const bool n_const = (slots % p.num_n_tiles == 0) || slots == total;
   if (d->stats_ws && slots % p.num_n_tiles != 0 && slots != total)
     return fail(FB_ERR_SHAPE, "stats need a grid that is a multiple of the N tiles");
+  if (d->bnbwd_z && (!d->bnbwd_coef || !d->stats_ws)) return fail(FB_ERR_ARG, "bnbwd_z needs bnbwd_coef and stats_ws");
+  // per-channel sums (BatchNorm moments / fused BatchNorm-backward reduce) of tiles with at most two chunks per epilogue warp
+  // run in the RS instantiation, whose epilogue has nothing else
+  const int rs = (d->stats_ws && (n_tile / 32) / (ew / 4) <= 2) ? 1 : 0;
+  if (rs && (d->pool_out || d->prod_out || d->head_out || d->scale || d->shift || d->relu || d->shift_in_acc || !d->store_main))
+    return fail(FB_ERR_ARG, "per-channel sums on %d-wide tiles come with the raw-accumulator epilogue only", n_tile);
   if (d->shift_in_acc && (d->scale || !d->shift)) return fail(FB_ERR_ARG, "shift_in_acc needs shift and no scale");
   if (d->shift_in_acc && !n_const) return fail(FB_ERR_SHAPE, "shift_in_acc needs one N tile per CTA");
 
@@ -111,7 +118,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   const int pool_tma = (d->pool_out && p.bh == 16) ? 1 : 0;
   const int prod_tma = (d->prod_out && out_bufs == 2 && !d->store_main) ? 1 : 0;
   const int fixed = out_bufs * 128 * n_tile * 2 + (pool_tma ? out_bufs * 4 * (n_tile / 64) * 1024 : 0) +
-                    fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr) + 1024;
+                    fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr, d->bnbwd_z != nullptr) + 1024;
   const int avail = smem_cap - fixed;
   const int kblocks = 9 * p.kchunks;
   int b_res = d->tune.b_resident;
@@ -144,6 +151,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   p.scale = d->scale, p.shift = d->shift;
   p.pool_out = reinterpret_cast<__nv_bfloat16*>(d->pool_out);
   p.stats_out = d->stats_ws;
+  p.bnb_z = reinterpret_cast<const __nv_bfloat16*>(d->bnbwd_z), p.bnb_coef = d->bnbwd_coef;
   p.head_w = d->head_w, p.head_b = d->head_b, p.head_out = d->head_out;
   p.prod_out = reinterpret_cast<__nv_bfloat16*>(d->prod_out), p.prod_ct = d->prod_channels, p.y0_ptr = d->y;
   p.pair_dates = d->prod_out ? 1 : 0;
@@ -152,13 +160,14 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   if ((double)p.num_m_tiles * p.num_n_tiles * 65536.0 >= 1.0e12) return fail(FB_ERR_SHAPE, "too many tiles");
   p.out_bufs = out_bufs, p.pool_tma = pool_tma, p.prod_tma = prod_tma;
   pl->n_tile = n_tile, pl->ck = ck, pl->halo = halo, pl->grid = grid, pl->smem = (int)smem, pl->ctas = ctas, pl->ew = ew, pl->minb = minb;
+  pl->rs = rs;
   return FB_OK;
 }
 
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1>
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1, bool RS = false>
 int launch_conv(const ConvPlan& pl, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tY,
                 const CUtensorMap& tP, const CUtensorMap& tQ, cudaStream_t st) {
-  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS, EW, MINB>;
+  auto k = fb::conv3x3_umma_kernel<N_TILE, CK, HALO, RES, CTAS, EW, MINB, RS>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid), cfg.blockDim = dim3(fb::conv_threads(EW)), cfg.dynamicSmemBytes = pl.smem, cfg.stream = st;
@@ -568,6 +577,7 @@ int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, 
   out->ctas = pl.ctas, out->epi_warps = pl.ew, out->a_stages = pl.p.a_stages, out->b_stages = pl.p.b_stages;
   out->b_resident = pl.p.b_resident, out->out_bufs = pl.p.out_bufs, out->total_units = pl.p.total_units;
   out->pool_tma = pl.p.pool_tma, out->prod_tma = pl.p.prod_tma, out->ctas_per_sm = pl.minb;
+  out->reg_stats = pl.rs;
   return FB_OK;
 }
 
@@ -619,8 +629,17 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
     if (pl.ctas == 2) return launch_conv<NT, CK, HL, RS, 2, EW>(pl, tA, tB, tY, tP, tQ, st);            \
     return launch_conv<NT, CK, HL, RS, 1, EW>(pl, tA, tB, tY, tP, tQ, st);                              \
   }
+  // the training instantiation (register statistics): CTA pairs only -- every training shape pairs up -- else one CTA
+#define FB_LAUNCH_RS(NT, CK, HL, RS, EW, MB)                                                            \
+  {                                                                                                     \
+    if (pl.ctas == 2) return launch_conv<NT, CK, HL, RS, 2, EW, MB, true>(pl, tA, tB, tY, tP, tQ, st);  \
+    return launch_conv<NT, CK, HL, RS, 1, EW, MB, true>(pl, tA, tB, tY, tP, tQ, st);                    \
+  }
 #define FB_DISPATCH(NT, CK, HL, RS)                                                                     \
   if (pl.n_tile == NT && pl.ck == CK && (pl.halo != 0) == HL && res == RS) {                            \
+    if (pl.rs && pl.ew == 8) FB_LAUNCH_RS(NT, CK, HL, RS, 8, 1)                                         \
+    if (pl.rs && NT == 64 && pl.minb == 2 && HL && RS) FB_LAUNCH_RS(64, CK, true, true, 4, 2)           \
+    if (pl.rs && NT == 64) FB_LAUNCH_RS(64, CK, HL, RS, 4, 1)                                           \
     if (pl.ew == 8) FB_LAUNCH(NT, CK, HL, RS, 8)                                                        \
     if (NT == 64 && HL && RS && pl.minb == 2) {                                                         \
       if (pl.ctas == 2) return launch_conv<64, CK, true, true, 2, 4, 2>(pl, tA, tB, tY, tP, tQ, st);    \
@@ -644,6 +663,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
   FB_DISPATCH4(256, 64, true, false)
 #undef FB_DISPATCH4
 #undef FB_LAUNCH
+#undef FB_LAUNCH_RS
 #undef FB_DISPATCH
   return fail(FB_ERR_SHAPE, "no kernel for n_tile %d ck %d halo %d resident %d", pl.n_tile, pl.ck, pl.halo, (int)res);
 }

@@ -39,6 +39,12 @@ struct Conv3x3Params {
   const float* shift;  // per out channel, nullable (=0)
   __nv_bfloat16* pool_out;  // nullable: 2x2 max-pooled copy [G,B,H/2,W/2,Cout]
   float* stats_out;         // nullable: per-CTA BN moment partials [grid][2][N_TILE][2] (sum, sum of squares)
+  // fused BatchNorm-backward reduce (data-gradient launches): the conv output is dL/da of the BatchNorm+ReLU whose
+  // pre-activation z is `bnb_z`; the epilogue applies the ReLU mask (z*scale+shift > 0), stores dy = mask * acc, and writes
+  // (sum dy, sum dy * xhat) partials into stats_out instead of the moments.  bnb_coef: fp32 [4][G][Cout] = scale, shift,
+  // mean, invstd of that BatchNorm.
+  const __nv_bfloat16* bnb_z;
+  const float* bnb_coef;
   const float* head_w;      // nullable: fused 1x1 head [2][64]
   const float* head_b;      // [2]
   float* head_out;          // [G*B, 2, H, W] fp32 NCHW
@@ -72,10 +78,11 @@ __host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) {
 }
 __host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
 __host__ __device__ constexpr int conv_stats_bytes(int N_TILE) { return 4 * 2 * N_TILE * 2 * 4; }
-__host__ __device__ constexpr int conv_misc_bytes(int N_TILE, bool stats) {
+__host__ __device__ constexpr int conv_bnb_bytes(int N_TILE) { return 2 * 4 * N_TILE * 4; }   // [2 groups][4][N_TILE] fp32
+__host__ __device__ constexpr int conv_misc_bytes(int N_TILE, bool stats, bool bnb = false) {
   // scale/shift + head weights (+ head exchange with two epilogue groups), stats slabs (only when BN moments are
-  // requested), barriers + tmem pointer
-  return (2 * N_TILE + 136 + 256) * 4 + (stats ? conv_stats_bytes(N_TILE) : 0) + 1024;
+  // requested), BatchNorm-backward coefficients, barriers + tmem pointer
+  return (2 * N_TILE + 136 + 256) * 4 + (stats ? conv_stats_bytes(N_TILE) : 0) + (bnb ? conv_bnb_bytes(N_TILE) : 0) + 1024;
 }
 
 // column sums over the 32 lanes of a warp: returns sum_lanes v[lane_id]  (31 shuffles instead of 160)
@@ -105,6 +112,32 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   float keep = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
+
+// one level of the same transposing tree: in[2W] -> out[W]; lane bit W decides which half of the columns this lane keeps
+template <int W>
+__device__ __forceinline__ void colsum_step(const float (&in)[2 * W], float (&out)[W], int lane) {
+  const bool b = lane & W;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const float keep = b ? in[i + W] : in[i], send = b ? in[i] : in[i + W];
+    out[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+  }
+}
+// the remaining levels: W values per lane -> the sum of column `lane`
+template <int W>
+__device__ __forceinline__ float colsum_finish(const float (&v)[W], int lane) {
+  if constexpr (W == 1) {
+    return v[0];
+  } else {
+    float o[W / 2];
+    colsum_step<W / 2>(v, o, lane);
+    return colsum_finish<W / 2>(o, lane);
+  }
+}
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
 
 struct TileCoord {
   int n0, x0, y0, b0, g;
@@ -151,7 +184,11 @@ __device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int N_TI
 
 // MINB = 2: two CTAs per SM (64-wide tiles with four epilogue warps only: 192 threads x 168 registers and <= 112 KB of
 // shared memory each) -- two independent tile pipelines per SM hide each other's per-tile latency chain
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1>
+// RS ("register statistics"): the training-step instantiation for tiles with at most two 32-column chunks per epilogue warp.
+// Its epilogue is raw-accumulator store (+ BatchNorm moments, or + the fused BatchNorm-backward reduce) only -- pooling,
+// product fusion, the 1x1 head, the affine / ReLU and accumulator-priming paths are compiled out -- and the per-channel sums
+// accumulate in registers across the CTA's tiles (see REGSTATS below).
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1, bool RS = false>
 __global__ void __launch_bounds__(conv_threads(EW), MINB)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP,
@@ -193,10 +230,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t pool_off = out_off + p.out_bufs * OUT_BYTES;
   const uint32_t ss_off = pool_off + (p.pool_tma ? p.out_bufs * POOL_BYTES : 0);
   const uint32_t st_off = ss_off + (2 * N_TILE + 136 + 256) * 4;
-  const uint32_t bar_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
+  const uint32_t bnb_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
+  const uint32_t bar_off = bnb_off + (p.bnb_z ? conv_bnb_bytes(N_TILE) : 0);
 
   float* ss = reinterpret_cast<float*>(sm + ss_off);       // [0,N) scale, [N,2N) shift, [2N,2N+128) head w, +128.. head b
   float* stats = reinterpret_cast<float*>(sm + st_off);    // [4 warps][2 groups][N_TILE][2]
+  float* bnb = reinterpret_cast<float*>(sm + bnb_off);     // [2 groups][4: scale, shift, mean, invstd][N_TILE]
   const uint32_t bars = base + bar_off;
   auto full_a = [&](int s) { return bars + 8u * s; };
   auto empty_a = [&](int s) { return bars + 8u * (p.a_stages + s); };
@@ -472,22 +511,69 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = etid; i < 128; i += kEpiThreads) ss[2 * N_TILE + i] = p.head_w[i];
       if (etid < 2) ss[2 * N_TILE + 128 + etid] = p.head_b[etid];
     }
+    if (p.bnb_z) {   // (the planner guarantees one N tile per CTA whenever partials are written)
+      TileCoord t0;
+      if (tile_at<CTAS>(p, 0, N_TILE, rank, t0)) {
+        for (int i = etid; i < 2 * 4 * N_TILE; i += kEpiThreads) {
+          const int g_ = i / (4 * N_TILE), k_ = (i / N_TILE) & 3, c_ = i % N_TILE;
+          bnb[i] = g_ < p.G ? p.bnb_coef[((size_t)k_ * p.G + g_) * p.Cout + t0.n0 + c_] : 0.f;
+        }
+      }
+    }
     const int px = m & 7;
     const int py = (m >> 3) % p.bh;
     const int pn = (m >> 3) / p.bh;
     // this warp's 4 tile rows (32 pixels) as a TMA store box: rows [wy, wy + min(bh,4)) of images [wn, ...)
     const int wn = (q * 4) / p.bh, wy = (q * 4) % p.bh;
-    const bool affine = !p.acc_init && (p.scale != nullptr || p.shift != nullptr);
-    const bool relu = p.relu != 0;
+    const bool affine = !RS && !p.acc_init && (p.scale != nullptr || p.shift != nullptr);
+    const bool relu = !RS && p.relu != 0;
     const bool extras = p.stats_out || p.pool_out || p.prod_out || p.head_out;   // one branch for the common plain tile
+    // moments in registers: with at most two 32-column chunks per warp the per-tile transposing shuffle tree (62 shuffles and
+    // ~250 selects / adds per chunk: measured +0.14 .. +0.28 ms on the 64- and 128-wide training convolutions) is replaced by
+    // plain per-thread accumulation over the CTA's tiles; the tree runs once per date group
+    constexpr int CPW = NCHUNK / kEpiGroups;          // chunks per warp
+    static_assert(!RS || CPW <= 2, "register statistics need at most two chunks per epilogue warp");
+    constexpr bool REGSTATS = RS;
+    constexpr int AW = REGSTATS ? 32 / CPW : 1;       // accumulators per chunk and moment
+    float acc1[REGSTATS ? CPW : 1][AW], acc2[REGSTATS ? CPW : 1][AW];
+#pragma unroll
+    for (int a_ = 0; a_ < (REGSTATS ? CPW : 1); ++a_)
+#pragma unroll
+      for (int j = 0; j < AW; ++j) acc1[a_][j] = acc2[a_][j] = 0.f;
+    int acc_g = -1;
+    auto flush_acc = [&](int g_) {
+      if constexpr (REGSTATS) {
+#pragma unroll
+        for (int sl = 0; sl < CPW; ++sl) {
+          const int cc = eg + sl * kEpiGroups;
+          const float c1 = colsum_finish<AW>(acc1[sl], lane), c2 = colsum_finish<AW>(acc2[sl], lane);
+          float* dst = my_stats + (g_ * N_TILE + cc * 32 + lane) * 2;
+          dst[0] += c1;
+          dst[1] += c2;
+#pragma unroll
+          for (int j = 0; j < AW; ++j) acc1[sl][j] = acc2[sl][j] = 0.f;
+        }
+      }
+    };
     // epilogue options as ONE opaque register: the chunk loop tests bits instead of re-reading kernel parameters through
     // the constant bank (LDCU + ISETP + BRA per test, each a latency bubble with one or two warps per scheduler)
     enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128,
-                      F_INIT = 256 };
-    uint32_t flags = (p.store_main ? F_MAIN : 0u) | (p.prod_out ? F_PROD : 0u) | (p.stats_out ? F_STATS : 0u) |
+                      F_INIT = 256, F_BNB = 512 };
+    uint32_t flags = (p.store_main ? F_MAIN : 0u) | (p.prod_out ? F_PROD : 0u) | ((p.stats_out && !p.bnb_z) ? F_STATS : 0u) |
+                     (p.bnb_z ? F_BNB : 0u) |
                      (p.pool_out ? F_POOL : 0u) | (p.pool_tma ? F_POOL_TMA : 0u) | (p.prod_tma ? F_PROD_TMA : 0u) |
                      (p.head_out ? F_HEAD : 0u) | (p.out_bufs == 2 ? F_TWO : 0u) | (p.acc_init ? F_INIT : 0u);
+    if constexpr (RS) flags &= (F_MAIN | F_STATS | F_BNB);   // the only epilogue options of the training instantiation
     asm volatile("mov.b32 %0, %0;" : "+r"(flags));
+    // flag test; in the RS instantiation every other option folds to false at compile time (its code and registers vanish)
+    auto has = [&](const uint32_t f) -> bool {
+      if constexpr (RS) {
+        if (!(f & (F_MAIN | F_STATS | F_BNB))) return false;
+      } else if constexpr (CPW <= 2) {
+        if (!(f & ~(F_STATS | F_BNB))) return false;   // per-channel sums of narrow tiles live in the RS instantiation only
+      }
+      return (flags & f) != 0u;
+    };
     const int pH = p.H, pW = p.W, pB = p.B, pCout = p.Cout, pCt = p.prod_ct;
     int cur_n0 = -1;
     uint32_t tile_it = 0;
@@ -512,7 +598,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tmem_st_32x32(tmem_base + acc_ * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), sv);
     };
-    if ((flags & F_INIT) && tile_at<CTAS>(p, 0, N_TILE, rank, tc)) {
+    if (has(F_INIT) && tile_at<CTAS>(p, 0, N_TILE, rank, tc)) {
       // (the planner guarantees one N tile per CTA in this mode, so the shift vector is loaded once)
       for (int i = etid; i < N_TILE; i += kEpiThreads) {
         ss[i] = 1.f;
@@ -549,12 +635,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bar_sync(1, kEpiThreads);
       }
       // output staging: with two buffers the previous tile stays readable in smem (date-0 tile of a product pair)
-      const int ob = (flags & F_TWO) ? (int)(tile_it & 1) : 0;
+      const int ob = has(F_TWO) ? (int)(tile_it & 1) : 0;
       uint8_t* out_sm = sm + out_off + ob * OUT_BYTES;
       const uint8_t* prev_sm = sm + out_off + (ob ^ 1) * OUT_BYTES;
-      const bool prod_tile = (flags & F_PROD) && tc.g == 1;
+      const bool prod_tile = has(F_PROD) && tc.g == 1;
       if (lane == 0) {   // this warp's own earlier stores
-        if ((flags & F_TWO)) tma_store_wait_read<1>();           // the store issued two tiles ago has drained this buffer
+        if (has(F_TWO)) tma_store_wait_read<1>();           // the store issued two tiles ago has drained this buffer
         else if (prod_tile) tma_store_wait_all<0>();             // single buffer: date-0 rows are re-read from L2
         else tma_store_wait_read<0>();
       }
@@ -563,13 +649,43 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
 
       float head0 = 0.f, head1 = 0.f;
-#pragma unroll 1
-      for (int cc = eg; cc < NCHUNK; cc += kEpiGroups) {
+      if constexpr (REGSTATS) {   // moments accumulate in registers per date group: hand them over when the group changes
+        if (has(F_STATS | F_BNB) && tc.g != acc_g) {
+          if (acc_g >= 0) flush_acc(acc_g);
+          acc_g = tc.g;
+        }
+      }
+      // one 32-column chunk of the tile; `slot_c` = which of this warp's chunks (compile time: indexes the accumulators)
+      auto do_chunk = [&](const int cc, auto slot_c) {
+        constexpr int SLOT = decltype(slot_c)::value;
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * N_TILE + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), r);
         tmem_ld_wait();
-        if (flags & F_INIT) preload_shift(acc, cc);   // the buffer's next tile starts from the shift again
+        if (has(F_INIT)) preload_shift(acc, cc);   // the buffer's next tile starts from the shift again
         uint32_t pk[16];
+        uint4 zq[4];   // (F_BNB) this pixel's 32 pre-activations z of the BatchNorm being differentiated
+        if (has(F_BNB)) {
+          if (valid) {
+            const uint4* zp = reinterpret_cast<const uint4*>(
+                p.bnb_z + ((((size_t)tc.g * pB + gb) * pH + gy) * pW + gx) * pCout + tc.n0 + cc * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zq[i] = __ldg(zp + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zq[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          // ReLU mask of the forward pass: relu'(z * scale + shift)
+          const float* cf = bnb + (tc.g * 4) * N_TILE + cc * 32;
+          const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
+                                   zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 sc = *reinterpret_cast<const float2*>(cf + 2 * j);
+            const float2 sh = *reinterpret_cast<const float2*>(cf + N_TILE + 2 * j);
+            if (!(fmaf(bf16_lo(zw[j]), sc.x, sh.x) > 0.f)) r[2 * j] = 0u;
+            if (!(fmaf(bf16_hi(zw[j]), sc.y, sh.y) > 0.f)) r[2 * j + 1] = 0u;
+          }
+        }
         if (affine) {
           float v[32];
 #pragma unroll
@@ -597,29 +713,78 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         // staging for the TMA store: sub-tile (cc/2) of 64 channels, row m, 16-byte chunk index XOR (m & 7)
         // (without a main output only the date-0 tile of a product pair is staged: its date-1 partner reads it back)
-        if ((flags & F_MAIN) || ((flags & F_PROD) && tc.g == 0)) {
+        if (has(F_MAIN) || (has(F_PROD) && tc.g == 0)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) *stage_ptr(out_sm, cc, i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
         if (extras) {
-        if ((flags & F_STATS)) {
-          // moments of the values as stored (bf16-rounded), invalid (out-of-image) pixels contribute 0
-          float s1[32], s2[32];
+        if (has(F_STATS | F_BNB)) {
+          // F_STATS: moments (sum x, sum x^2) of the values as stored (bf16-rounded); F_BNB: (sum dy, sum dy * xhat) of the
+          // masked gradient as stored.  Invalid (out-of-image) pixels contribute 0.
+          // value / weight pairs: (x, x) for the moments, (dy, xhat) for the backward sums: s1 = v, s2 = v * wv
+          auto load_v = [&](float (&v)[32]) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float lo = valid ? bf16_lo(pk[j]) : 0.f, hi = valid ? bf16_hi(pk[j]) : 0.f;
-            s1[2 * j] = lo;
-            s1[2 * j + 1] = hi;
-            s2[2 * j] = lo * lo;
-            s2[2 * j + 1] = hi * hi;
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+              v[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+            }
+          };
+          auto mul_w = [&](float (&v)[32]) {   // v <- v * (x or xhat)
+            if (has(F_BNB)) {
+              const float* cf = bnb + (tc.g * 4 + 2) * N_TILE + cc * 32;   // mean, then invstd
+              const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
+                                       zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 mu = *reinterpret_cast<const float2*>(cf + 2 * j);
+                const float2 is = *reinterpret_cast<const float2*>(cf + N_TILE + 2 * j);
+                v[2 * j] *= (bf16_lo(zw[j]) - mu.x) * is.x;
+                v[2 * j + 1] *= (bf16_hi(zw[j]) - mu.y) * is.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= v[j];
+            }
+          };
+          if constexpr (REGSTATS) {
+            // no (CPW = 1) or one (CPW = 2) level of the transposing tree per tile; the rest once per date group.  The two
+            // sums are processed one after the other to keep the live register set small.
+            float v[32];
+            load_v(v);
+            if constexpr (AW == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc1[SLOT][j] += v[j];
+            } else {
+              float t[16];
+              colsum_step<16>(v, t, lane);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc1[SLOT][j] += t[j];
+            }
+            load_v(v);
+            mul_w(v);
+            if constexpr (AW == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc2[SLOT][j] += v[j];
+            } else {
+              float t[16];
+              colsum_step<16>(v, t, lane);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc2[SLOT][j] += t[j];
+            }
+          } else {
+            float s1[32], s2[32];
+            load_v(s1);
+            load_v(s2);
+            mul_w(s2);
+            const float cs1 = warp_colsum32(s1, lane);
+            const float cs2 = warp_colsum32(s2, lane);
+            float* dst = my_stats + (tc.g * N_TILE + cc * 32 + lane) * 2;
+            dst[0] += cs1;
+            dst[1] += cs2;
           }
-          const float cs1 = warp_colsum32(s1, lane);
-          const float cs2 = warp_colsum32(s2, lane);
-          float* dst = my_stats + (tc.g * N_TILE + cc * 32 + lane) * 2;
-          dst[0] += cs1;
-          dst[1] += cs2;
         }
-        if ((flags & F_POOL)) {
+        if constexpr (!RS) {
+        if (has(F_POOL)) {
           // 2x2 max over (x^1, y^1) neighbours = lanes ^1 and ^8 of the same warp
           uint32_t pm[16];
 #pragma unroll
@@ -628,7 +793,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             pm[j] = bf16x2_max(a, __shfl_xor_sync(0xffffffffu, a, 8));
           }
           const int Hp = pH >> 1, Wp = pW >> 1;
-          if ((flags & F_POOL_TMA)) {
+          if (has(F_POOL_TMA)) {
             // this warp's 4 tile rows x 8 columns pool to 2 x 4 pixels: row r of a 128B-swizzled [8][64 ch] slab per
             // 64-channel group; the TMA store clips whatever lies outside the pooled image
             if (!(lane & 9)) {   // even column, even row
@@ -648,7 +813,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2], pm[4 * i + 3]);
           }
         }
-        if (prod_tile && (valid || (flags & F_PROD_TMA))) {
+        if (prod_tile && (valid || has(F_PROD_TMA))) {
           // relu(d2 * d1): this tile is date 1; the same CTA produced the date-0 tile one iteration ago.  With two
           // staging buffers this thread re-reads ITS OWN row of that tile from smem, otherwise from L2.
           const size_t pix = ((size_t)gb * pH + gy) * pW + gx;
@@ -657,17 +822,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint4* dst = reinterpret_cast<uint4*>(p.prod_out + pix * pCt + tc.n0 + cc * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 o = (flags & F_TWO) ? *stage_ptr(const_cast<uint8_t*>(prev_sm), cc, i) : __ldcg(a0 + i);
+            const uint4 o = has(F_TWO) ? *stage_ptr(const_cast<uint8_t*>(prev_sm), cc, i) : __ldcg(a0 + i);
             // packed bf16 multiply: the fp32 product of two bf16 values is exact, so one rounding either way
             const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
             uint32_t rv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) rv[k] = bf16x2_max(bf16x2_mul(pk[4 * i + k], ov[k]), 0u);
-            if ((flags & F_PROD_TMA)) *stage_ptr(out_sm, cc, i) = make_uint4(rv[0], rv[1], rv[2], rv[3]);   // date-1 tile's own buffer
+            if (has(F_PROD_TMA)) *stage_ptr(out_sm, cc, i) = make_uint4(rv[0], rv[1], rv[2], rv[3]);   // date-1 tile's own buffer
             else dst[i] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
           }
         }
-        if ((flags & F_HEAD)) {
+        if (has(F_HEAD)) {
           const float* hw = ss + 2 * N_TILE;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -678,10 +843,18 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             head1 = fmaf(hi, hw[64 + cc * 32 + 2 * j + 1], head1);
           }
         }
+        }  // !RS
         }  // extras
+      };
+      if constexpr (REGSTATS) {
+        do_chunk(eg, IntC<0>{});
+        if constexpr (CPW == 2) do_chunk(eg + kEpiGroups, IntC<1>{});
+      } else {
+#pragma unroll 1
+        for (int cc = eg; cc < NCHUNK; cc += kEpiGroups) do_chunk(cc, IntC<0>{});
       }
       // accumulator drained (and re-primed) -> MMA may overwrite it
-      if (flags & F_INIT) tmem_st_wait();
+      if (has(F_INIT)) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -689,7 +862,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else mbar_arrive(tmem_empty(acc));
       }
 
-      if (kEpiGroups == 2 && (flags & F_HEAD)) {   // each group summed its own 32 channels: group 1 hands its part to group 0
+      if (kEpiGroups == 2 && has(F_HEAD)) {   // each group summed its own 32 channels: group 1 hands its part to group 0
         if (eg == 1) {
           hx[2 * m] = head0;
           hx[2 * m + 1] = head1;
@@ -701,7 +874,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         bar_sync(2 + q, 64);   // hx is free again before group 1 reaches the next tile
       }
-      if ((flags & F_HEAD) && valid && eg == 0) {
+      if (has(F_HEAD) && valid && eg == 0) {
         const float* hb = ss + 2 * N_TILE + 128;
         const size_t img = (size_t)tc.g * pB + gb;
         const size_t plane = (size_t)pH * pW;
@@ -719,9 +892,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int cc = 2 * j + eg;   // (EW = 8) chunk of box j
           const uint32_t src = kEpiGroups == 1 ? obuf + j * 16384 + q * 4096 : obuf + cc * 8192 + q * 2048;
           const int ch = tc.n0 + (kEpiGroups == 1 ? j * 64 : cc * 32);
-          if ((flags & F_MAIN)) tma_store_5d(&tmY, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, tc.g);
-          if ((flags & F_PROD_TMA) && tc.g == 1) tma_store_5d(&tmP, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, 0);
-          if ((flags & F_POOL_TMA))
+          if (has(F_MAIN)) tma_store_5d(&tmY, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, tc.g);
+          if (has(F_PROD_TMA) && tc.g == 1) tma_store_5d(&tmP, src, ch, tc.x0, tc.y0 + wy, tc.b0 + wn, 0);
+          if (has(F_POOL_TMA))
             tma_store_5d(&tmQ, kEpiGroups == 1 ? pbuf + j * 1024 : pbuf + cc * 512, ch, tc.x0 >> 1, (tc.y0 >> 1) + 2 * q, tc.b0,
                          tc.g);
         }
@@ -729,6 +902,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
+    if constexpr (REGSTATS) {
+      if (acc_g >= 0) flush_acc(acc_g);
+    }
     if (p.stats_out) {
       bar_sync(1, kEpiThreads);
       // partial index i with i % num_n_tiles == this CTA's N tile (what bn_finalize assumes): a pair's two CTAs sit

@@ -340,6 +340,7 @@ struct BnBwd {
   const float* invstd;
   int ga_groups, ga_c8, mul_other;
   int G, B, H, W, C;
+  int premasked;   // ga already is dy = relu'(.) * dL/da (written by the producing kernel's epilogue): no mask here
 };
 
 // dy for the 8 channels c8 of pixel `pix` (index inside one date group: (b*H + y)*W + x) of date group g.
@@ -408,9 +409,11 @@ __device__ __forceinline__ void bn_bwd_finish(const BnBwd& p, uint32_t g, uint32
         if (best[j] == (int)me) dy[j] += gpv[j];
     }
   }
+  if (!p.premasked) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (!(fmaf(zf[j], sc[j], sh[j]) > 0.f)) dy[j] = 0.f;
+    for (int j = 0; j < 8; ++j)
+      if (!(fmaf(zf[j], sc[j], sh[j]) > 0.f)) dy[j] = 0.f;
+  }
 }
 
 // pass 1: partial[blk][g][c][2] = (sum dy, sum dy * xhat)
@@ -462,16 +465,26 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwd p, float* _
 }
 
 // pass 2: reduce partials (one warp per channel); dgamma, dbeta; per-group coefficients for the apply pass
+// n_tile == 0: partial[blk][G][C][2] (the stand-alone reduce kernels); n_tile > 0: the conv epilogue's layout
+// partial[cta][2][n_tile][2], where CTA i holds N tile i % (C / n_tile) (fabric_b200_conv3x3 with bnbwd_z).
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int G, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        const float* __restrict__ mean, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef, float grad_scale) {
+                                       float* __restrict__ dbeta, float* __restrict__ coef, float grad_scale, int n_tile = 0) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double dg = 0.0, db = 0.0;
   for (int g = 0; g < G; ++g) {
     double s1 = 0.0, s2 = 0.0;
+    if (n_tile > 0) {
+      const int ntiles = C / n_tile, nt = c / n_tile, lc = c % n_tile;
+      for (int cta = nt + lane * ntiles; cta < nblk; cta += 32 * ntiles) {
+        const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)cta * 2 + g) * n_tile + lc) * 2);
+        s1 += v.x;
+        s2 += v.y;
+      }
+    } else
     for (int b = lane; b < nblk; b += 32) {
       const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * G + g) * C + c) * 2);
       s1 += v.x;
@@ -959,6 +972,7 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   p.scale = scale, p.shift = shift, p.mean = mean, p.invstd = invstd;
   p.ga_groups = ga_groups, p.ga_c8 = ga_channels / 8, p.mul_other = mul_other;
   p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
+  p.premasked = 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = di.sms * 2;   // = resident blocks (256 threads, 2 per SM): one balanced wave
   float* partial = ws;
@@ -999,6 +1013,33 @@ int fabric_b200_bn_relu_bwd_phase(int phase, const void* z, const void* a, const
   if (phase != 1 && phase != 2) return fail(FB_ERR_ARG, "phase must be 1 (reduce) or 2 (finalize + apply)");
   return bn_relu_bwd_phases(phase, z, a, ga, ga_groups, ga_channels, mul_other, gp, scale, shift, mean, invstd, gamma, dz,
                             dgamma, dbeta, ws, G, B, H, W, C, count_scale, grad_scale, stream);
+}
+
+int fabric_b200_bn_bwd_from_partials(const void* z, const void* dy, const float* partial, int grid, int n_tile,
+                                     const float* mean, const float* invstd, const float* gamma, void* dz, float* dgamma,
+                                     float* dbeta, float* coef_ws, int G, int B, int H, int W, int C, float count_scale,
+                                     float grad_scale, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!z || !dy || !partial || !mean || !invstd || !gamma || !dz || !dgamma || !dbeta || !coef_ws) return fail(FB_ERR_ARG, "null pointer");
+  if (C % 8 || 256 % (C / 8) || n_tile < 32 || C % n_tile || grid < C / n_tile || G < 1 || G > 2) return fail(FB_ERR_SHAPE, "bad shape");
+  if ((double)G * B * H * W * C / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
+  BnBwd p;
+  p.z = reinterpret_cast<const uint4*>(z), p.a = nullptr;
+  p.ga = reinterpret_cast<const uint4*>(dy), p.gp = nullptr;
+  p.scale = mean, p.shift = mean, p.mean = mean, p.invstd = invstd;   // (scale / shift are not read: dy is pre-masked)
+  p.ga_groups = G, p.ga_c8 = C / 8, p.mul_other = 0;
+  p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
+  p.premasked = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, grid, G, C, (double)B * H * W * (double)count_scale, gamma, invstd,
+                                                      mean, dgamma, dbeta, coef_ws, grad_scale, n_tile);
+  FB_CUDA(cudaGetLastError());
+  const size_t n = (size_t)B * H * W * (C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef_ws, reinterpret_cast<uint4*>(dz));
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
 }
 
 int64_t fabric_b200_bn_bwd_partial_floats(int G, int C) {

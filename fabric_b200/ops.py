@@ -222,7 +222,7 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
             shift: Optional[torch.Tensor] = None, relu: bool = False, pool: bool = False, stats: bool = False,
             head=None, store_main: bool = True, tune: Optional[dict] = None, out: Optional[torch.Tensor] = None,
             true_cin: Optional[int] = None, prod_out: Optional[torch.Tensor] = None, shift_in_acc: bool = False,
-            tag: Optional[str] = None):
+            tag: Optional[str] = None, bnbwd=None):
     """3x3 pad-1 convolution on tcgen05 (see include/fabric_b200.h: fabric_b200_conv3x3).
 
     Returns a dict with ``y`` [G,B,H,W,cout] bf16 and optionally ``pool`` [G,B,H/2,W/2,cout],
@@ -258,6 +258,15 @@ def conv3x3(x5: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional
         # fused relu(y[date 1] * y[date 0]) into channels [0, cout) of the decoder input [1,B,H,W,Ct]
         assert g == 2 and prod_out.shape[:4] == (1, b, h, w) and prod_out.dtype == torch.bfloat16
         d.prod_out, d.prod_channels = _p(prod_out), prod_out.shape[4]
+    if bnbwd is not None:
+        # data-gradient launch with the BatchNorm-backward reduce fused into its epilogue: bnbwd = (z5, BnCoef) of the
+        # BatchNorm + ReLU this conv's output is the gradient of; y becomes dy (masked), res["stats"] the (sum dy, sum dy*xhat)
+        # partials for bn_bwd_from_partials
+        zb, coef = bnbwd
+        _need_cuda(zb, coef.base)
+        assert zb.shape == (g, b, h, w, cout) and zb.dtype == torch.bfloat16 and coef.base.shape == (4, g, cout)
+        d.bnbwd_z, d.bnbwd_coef = _p(zb), _p(coef.base)
+        stats = True
     if stats:
         # the workspace size depends on the grid the planner picks; the planner ignores the pointer value
         d.stats_ws = 1
@@ -320,13 +329,21 @@ def outconv(x5: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
 WGRAD_WIDE = 3
 
 
+class BnCoef(tuple):
+    """(scale, shift, mean, invstd), each [G,C] fp32, as views of ONE [4,G,C] buffer (``.base``): the layout the fused
+    BatchNorm-backward epilogue of the data-gradient conv reads (fb_conv3x3_desc.bnbwd_coef)."""
+    base: torch.Tensor
+
+
 def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_per_group: int, groups: int):
     """Finish train-mode BatchNorm from the conv epilogue's moment partials; updates the running statistics in
     place (momentum, unbiased variance, num_batches_tracked += groups).  Returns (scale, shift, mean, invstd) [G,C]."""
     grid, _, n_tile, _ = stats.shape
     c = bn.num_features
     dev = stats.device
-    out = [_empty((groups, c), dtype=torch.float32, device=dev) for _ in range(4)]
+    base = _empty((4, groups, c), dtype=torch.float32, device=dev)
+    out = BnCoef(base[i] for i in range(4))
+    out.base = base
     mom = 0.1 if bn.momentum is None else float(bn.momentum)
     if EXACT is not None and EXACT.world > 1:
         # every rank launched the same grid: the element-wise SUM of the per-CTA partial arrays is a valid partial array of
@@ -438,6 +455,28 @@ def bn_relu_bwd(z5, a5, ga, mul_other, gp, scale, shift, mean, invstd, gamma, dg
                                       _p(mean), _p(invstd), _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws),
                                       g, b, h, w, c, _stream()), "bn_relu_bwd")
     _count(3)
+    return dz, dgamma, dbeta
+
+
+def bn_bwd_from_partials(z5, dy5, partial, coef: BnCoef, gamma, dgamma_out=None, dbeta_out=None):
+    """BatchNorm(train)+ReLU backward when the producing data-gradient conv already masked (dy5) and reduced (partial, the
+    conv's ``res["stats"]`` view [grid,2,n_tile,2]): ONE pass over (dy, z).  Returns (dz, dgamma, dbeta)."""
+    g, b, h, w, c = z5.shape
+    lib = _lib.load()
+    _need_cuda(z5, dy5, partial, dgamma_out, dbeta_out)
+    grid, _, n_tile, _ = partial.shape
+    dz = _empty_like(z5)
+    dgamma = dgamma_out if dgamma_out is not None else _empty(c, dtype=torch.float32, device=z5.device)
+    dbeta = dbeta_out if dbeta_out is not None else _empty(c, dtype=torch.float32, device=z5.device)
+    ws = _empty(g * 3 * c, dtype=torch.float32, device=z5.device)
+    count_scale = grad_scale = 1.0
+    if EXACT is not None and EXACT.world > 1:
+        EXACT.all_reduce(partial)
+        count_scale, grad_scale = float(EXACT.world), 1.0 / EXACT.world
+    check(lib.fabric_b200_bn_bwd_from_partials(_p(z5), _p(dy5), _p(partial), grid, n_tile, _p(coef[2]), _p(coef[3]),
+                                               _p(gamma.detach()), _p(dz), _p(dgamma), _p(dbeta), _p(ws), g, b, h, w, c,
+                                               count_scale, grad_scale, _stream()), "bn_bwd_from_partials")
+    _count(2)
     return dz, dgamma, dbeta
 
 

@@ -102,6 +102,15 @@ typedef struct {
   int shift_in_acc;    /* 1: the accumulator starts at shift[] (scale must be NULL, i.e. folded into w): y = acc + shift.
                           The epilogue is then convert (+ReLU) + store; the epilogue warps re-prime TMEM after each tile */
   fb_conv_tuning tune;
+  /* Fused BatchNorm-backward reduce, for the data-gradient launch whose output is dL/da of a training-mode
+   * BatchNorm2d + ReLU (unet_parts.py:14-15 as seen by autograd): bnbwd_z = that layer's pre-activation z, bf16
+   * [G][B][H][W][Cout]; bnbwd_coef = fp32 [4][G][Cout] (scale, shift, mean, invstd from fabric_b200_bn_finalize).  The
+   * epilogue stores dy = relu'(z*scale+shift) * acc instead of acc and writes per-CTA (sum dy, sum dy*xhat) partials into
+   * stats_ws (same layout and size as the moment partials), which fabric_b200_bn_bwd_from_partials finishes -- the
+   * stand-alone reduce pass over (dL/da, z) disappears.  Raw-accumulator epilogue only (no scale / shift / relu / pool /
+   * head / product). */
+  const void* bnbwd_z;
+  const float* bnbwd_coef;
 } fb_conv3x3_desc;
 
 /* y = conv3x3(x, w) * scale + shift (+ReLU) (+pool) (+BN moment partials) (+1x1 head).
@@ -113,6 +122,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream);
 typedef struct {
   int n_tile, ck, halo, grid, smem_bytes, ctas, epi_warps, a_stages, b_stages, b_resident, out_bufs, total_units;
   int pool_tma, prod_tma, ctas_per_sm;
+  int reg_stats;   /* 1: per-channel sums accumulate in registers across the CTA's tiles (training instantiation) */
 } fb_conv3x3_plan;
 int fabric_b200_conv3x3_plan(const fb_conv3x3_desc* d, int sms, int smem_optin, fb_conv3x3_plan* out);
 /* grid the launch above will use, and the stats workspace size (floats) for it */
@@ -207,6 +217,16 @@ int fabric_b200_bn_relu_bwd_phase(int phase, const void* z, const void* a, const
                                   int mul_other, const void* gp, const float* scale, const float* shift, const float* mean,
                                   const float* invstd, const float* gamma, void* dz, float* dgamma, float* dbeta, float* ws,
                                   int G, int B, int H, int W, int C, float count_scale, float grad_scale, void* stream);
+
+/* BatchNorm(train) + ReLU backward when the producer of dL/da already did the reduce: `dy` = relu'(.) * dL/da (bf16) and
+ * `partial` = per-CTA (sum dy, sum dy*xhat) in the conv epilogue's layout [grid][2][n_tile][2], both written by the
+ * data-gradient launch of fabric_b200_conv3x3 with bnbwd_z set.  Finishes dgamma / dbeta and writes
+ * dz = gamma*invstd * (dy - mean(dy) - xhat*mean(dy*xhat)) in ONE pass over (dy, z).  coef_ws: G*3*C floats.
+ * count_scale / grad_scale as in fabric_b200_bn_relu_bwd_phase (exact-global mode all-reduces `partial` first). */
+int fabric_b200_bn_bwd_from_partials(const void* z, const void* dy, const float* partial, int grid, int n_tile,
+                                     const float* mean, const float* invstd, const float* gamma, void* dz, float* dgamma,
+                                     float* dbeta, float* coef_ws, int G, int B, int H, int W, int C, float count_scale,
+                                     float grad_scale, void* stream);
 
 /* adjoint of the upsample half of fabric_b200_build_up_input: dcat [B][H][W][Cs+Cl] -> dlow [B][h][w][Cl] */
 int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream);

@@ -17,10 +17,10 @@ def plan(lib, G, B, H, W, cin, cout, **kw):
     from fabric_b200 import _lib
     d = _lib.Conv3x3Desc()
     d.G, d.B, d.H, d.W, d.Cin, d.Cout = G, B, H, W, (16 if cin <= 16 else cin), cout
-    d.relu, d.store_main = 1, int(kw.get("store_main", 1))
+    d.relu, d.store_main = int(kw.get("relu", 1)), int(kw.get("store_main", 1))
     d.x = d.w = 0x1000
     d.y = 0x1000 if d.store_main else None
-    for k in ("pool_out", "stats_ws", "prod_out", "head_out", "head_w", "head_b", "shift", "scale"):
+    for k in ("pool_out", "stats_ws", "prod_out", "head_out", "head_w", "head_b", "shift", "scale", "bnbwd_z", "bnbwd_coef"):
         if kw.get(k):
             setattr(d, k, 0x1000)
     d.prod_channels = kw.get("prod_channels", 0)
@@ -41,20 +41,27 @@ LAYERS = [("inc.c1", 2, 256, 13, 64), ("inc.c2", 2, 256, 64, 64), ("down1.c1", 2
 
 
 @pytest.mark.parametrize("name,G,H,cin,cout", LAYERS)
-@pytest.mark.parametrize("mode", ["eval", "train_fwd", "dgrad"])
+@pytest.mark.parametrize("mode", ["eval", "train_fwd", "dgrad", "dgrad_bnbwd"])
 def test_every_layer_has_a_valid_pair_plan(lib, name, G, H, cin, cout, mode):
     kw = {}
     if mode == "eval":
         kw = dict(shift=1, shift_in_acc=1)
     elif mode == "train_fwd":
-        kw = dict(stats_ws=1)
+        kw = dict(stats_ws=1, relu=0)           # raw accumulator + BatchNorm moment partials
     else:
+        kw = dict(relu=0)
+        if mode == "dgrad_bnbwd":               # data gradient of c2 with the BatchNorm-1 backward reduce in its epilogue
+            if not name.endswith(".c2"):
+                pytest.skip("only the second conv's data gradient feeds a BatchNorm backward")
+            kw.update(stats_ws=1, bnbwd_z=1, bnbwd_coef=1)
         if cin == 13:
             pytest.skip("the stem needs no data gradient")
         cin, cout = cout, cin           # the data gradient is the same kernel with the channel roles swapped
     rc, p = plan(lib, G, 64, H, H, cin, cout, **kw)
     assert rc == 0, lib.fabric_b200_last_error()
     assert p.smem_bytes <= SMEM
+    # per-channel sums of the 64- and 128-wide tiles accumulate in registers (training instantiation)
+    assert p.reg_stats == (1 if "stats_ws" in kw and p.n_tile <= 128 else 0)
     assert p.ctas == 2 and p.grid % 2 == 0                            # CTA pairs on every real layer
     assert p.n_tile == (64 if cout == 64 else 256 if cout % 256 == 0 else 128)
     stem = cin <= 16

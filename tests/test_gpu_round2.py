@@ -681,3 +681,69 @@ def test_graphed_train_step_equals_eager_steps(cuda, batch, size):
     with torch.no_grad():
         assert torch.equal(graphed(batches[0][0], batches[0][1]), eager(batches[0][0], batches[0][1]))
     dp_g.close()
+
+
+# ------------------------------------------------------------------------------------------------ fused BatchNorm backward
+@pytest.mark.parametrize("G,B,H,W,cin,cout", [(2, 3, 20, 12, 128, 64), (1, 2, 32, 24, 64, 128), (2, 2, 16, 16, 256, 256),
+                                              (1, 5, 7, 9, 64, 64)])
+def test_dgrad_epilogue_bn_backward_reduce_matches_standalone_kernels(cuda, G, B, H, W, cin, cout):
+    """fabric_b200_conv3x3 with bnbwd_z: the epilogue's masked output equals relu'(bn(z)) * (plain conv output) bit for bit,
+    its partials sum to (sum dy, sum dy*xhat), and fabric_b200_bn_bwd_from_partials gives the dz / dgamma / dbeta of the
+    stand-alone reduce + apply kernels (fp32 summation order aside) -- all three tile widths (64 / 128 in the register-
+    accumulating instantiation, 256 through the shuffle tree) and a ragged map."""
+    from fabric_b200 import ops
+    torch.manual_seed(12)
+    x5 = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()             # plays dL/dz2
+    wq = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=cuda) / (3 * cin ** 0.5), 0)
+    z5 = torch.randn(G, B, H, W, cout, device=cuda).bfloat16()            # pre-activation of the BatchNorm being differentiated
+    bn = torch.nn.BatchNorm2d(cout).to(cuda)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.3)
+    zf = z5.float()
+    mean = zf.mean((1, 2, 3))
+    var = zf.var((1, 2, 3), unbiased=False)
+    invstd = torch.rsqrt(var + 1e-5)
+    scale = bn.weight[None] * invstd
+    shift = bn.bias[None] - mean * scale
+    base = torch.stack([scale, shift, mean, invstd]).contiguous()
+    coef = ops.BnCoef(base[i] for i in range(4))
+    coef.base = base
+    plain = ops.conv3x3(x5, wq, cout)["y"]
+    fused = ops.conv3x3(x5, wq, cout, bnbwd=(z5, coef))
+    mask = (zf * scale[:, None, None, None] + shift[:, None, None, None]) > 0
+    want_dy = torch.where(mask, plain.float(), torch.zeros((), device=cuda)).bfloat16()
+    assert torch.equal(fused["y"], want_dy)
+    part = fused["stats"]                                                 # [grid, 2, n_tile, 2], CTA i holds N tile i % ntiles
+    grid, _, n_tile, _ = part.shape
+    nt = cout // n_tile
+    sums = part.view(grid // nt, nt, 2, n_tile, 2).double().sum(0).permute(1, 0, 2, 3).reshape(2, cout, 2)[:G]
+    dyf = want_dy.double()
+    xhat = (zf.double() - mean.double()[:, None, None, None]) * invstd.double()[:, None, None, None]
+    assert rel(sums[..., 0], dyf.sum((1, 2, 3))) <= 1e-4 and rel(sums[..., 1], (dyf * xhat).sum((1, 2, 3))) <= 1e-4
+    dz_f, dg_f, db_f = ops.bn_bwd_from_partials(z5, fused["y"], part, coef, bn.weight)
+    dz_s, dg_s, db_s = ops.bn_relu_bwd(z5, None, plain, False, None, scale, shift, mean, invstd, bn.weight)
+    assert rel(dg_f, dg_s) <= 1e-4 and rel(db_f, db_s) <= 1e-4
+    assert rel(dz_f.float(), dz_s.float()) <= 2e-3                        # bf16 re-rounding of a few elements
+    assert (dz_f != dz_s).float().mean().item() <= 0.02
+
+
+def test_training_step_with_and_without_fused_bn_backward_reduce_agree(cuda):
+    """whole step (config 1 and an odd-size batch): FUSE_BN_BWD_REDUCE on / off give the same loss and gradients up to the
+    fp32 summation order of the (sum dy, sum dy*xhat) pairs"""
+    from fabric_b200 import autograd
+    from oracle import bidatenet_oracle as O
+    for (b, s_, seed) in ((2, 32, 1), (3, 90, 2)):
+        x1, x2, labels = (t.to(cuda) for t in O.make_inputs(b, s_, seed=seed))
+        res = []
+        for fuse in (True, False):
+            autograd.FUSE_BN_BWD_REDUCE = fuse
+            try:
+                model = _model(cuda)
+                loss = _step(model, x1, x2, labels)
+                res.append((loss, _grads(model)))
+            finally:
+                autograd.FUSE_BN_BWD_REDUCE = True
+        assert torch.equal(res[0][0], res[1][0])
+        worst = max((rel(res[0][1][k], res[1][1][k]), k) for k in res[0][1] if float(res[1][1][k].abs().max()) > 0)
+        print("fused vs stand-alone BN backward reduce:", (b, s_), worst)
+        assert worst[0] <= 1e-2, worst
