@@ -56,7 +56,9 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None):
     # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
     grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
     grads[b2.weight], grads[b2.bias] = dg2, db2
-    if FUSE_BN_BWD_REDUCE:
+    # (fused for the 64- and 128-wide layers -- the big tensors; on the 256-wide tiles the epilogue reads z with plain
+    #  loads and the fusion measured slower than the stand-alone reduce pass over those small maps)
+    if FUSE_BN_BWD_REDUCE and dc.out_ch <= 128:
         r = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad", bnbwd=(sv["z1"], sv["s1"]))
         del dz2
         dz1, dg1, db1 = ops.bn_bwd_from_partials(sv["z1"], r["y"], r["stats"], sv["s1"], b1.weight,

@@ -79,6 +79,9 @@ __host__ __device__ constexpr int conv_a_stage_bytes(int CK, bool halo) {
 __host__ __device__ constexpr int conv_b_stage_bytes(int N_TILE, int CK) { return N_TILE * CK * 2; }
 __host__ __device__ constexpr int conv_stats_bytes(int N_TILE) { return 4 * 2 * N_TILE * 2 * 4; }
 __host__ __device__ constexpr int conv_bnb_bytes(int N_TILE) { return 2 * 4 * N_TILE * 4; }   // [2 groups][4][N_TILE] fp32
+// (RS + fused BatchNorm-backward reduce) z prefetch slots: one 64-byte row (+16 bytes of padding against bank conflicts) per
+// epilogue thread and chunk, filled by cp.async one tile ahead
+__host__ __device__ constexpr int conv_zbuf_bytes(int N_TILE, int EW) { return EW * 32 * ((N_TILE / 32) / (EW / 4)) * 80; }
 __host__ __device__ constexpr int conv_misc_bytes(int N_TILE, bool stats, bool bnb = false) {
   // scale/shift + head weights (+ head exchange with two epilogue groups), stats slabs (only when BN moments are
   // requested), BatchNorm-backward coefficients, barriers + tmem pointer
@@ -231,7 +234,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t ss_off = pool_off + (p.pool_tma ? p.out_bufs * POOL_BYTES : 0);
   const uint32_t st_off = ss_off + (2 * N_TILE + 136 + 256) * 4;
   const uint32_t bnb_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
-  const uint32_t bar_off = bnb_off + (p.bnb_z ? conv_bnb_bytes(N_TILE) : 0);
+  const uint32_t zbuf_off = bnb_off + (p.bnb_z ? conv_bnb_bytes(N_TILE) : 0);
+  const uint32_t bar_off = zbuf_off + ((RS && p.bnb_z) ? conv_zbuf_bytes(N_TILE, EW) : 0);
 
   float* ss = reinterpret_cast<float*>(sm + ss_off);       // [0,N) scale, [N,2N) shift, [2N,2N+128) head w, +128.. head b
   float* stats = reinterpret_cast<float*>(sm + st_off);    // [4 warps][2 groups][N_TILE][2]
@@ -566,13 +570,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (RS) flags &= (F_MAIN | F_STATS | F_BNB);   // the only epilogue options of the training instantiation
     asm volatile("mov.b32 %0, %0;" : "+r"(flags));
     // flag test; in the RS instantiation every other option folds to false at compile time (its code and registers vanish)
+    // (per-channel sums of narrow tiles live in the RS instantiation only; the 13-band stem has no data gradient)
+    constexpr uint32_t kAllowed = (RS ? (F_MAIN | F_STATS | F_BNB) : (CPW <= 2 ? ~(F_STATS | F_BNB) : ~0u)) &
+                                  (CK == 16 ? ~static_cast<uint32_t>(F_BNB) : ~0u);
     auto has = [&](const uint32_t f) -> bool {
-      if constexpr (RS) {
-        if (!(f & (F_MAIN | F_STATS | F_BNB))) return false;
-      } else if constexpr (CPW <= 2) {
-        if (!(f & ~(F_STATS | F_BNB))) return false;   // per-channel sums of narrow tiles live in the RS instantiation only
-      }
-      return (flags & f) != 0u;
+      if ((f & kAllowed) == 0u) return false;
+      return (flags & f & kAllowed) != 0u;
     };
     const int pH = p.H, pW = p.W, pB = p.B, pCout = p.Cout, pCt = p.prod_ct;
     int cur_n0 = -1;
@@ -620,6 +623,29 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    // (RS, F_BNB) this thread's z row of chunk slot `sl` of tile `it_` -> its smem slot, asynchronously (cp.async): issued one
+    // tile ahead, right after the slot's previous contents were consumed, so the global-load latency (the first version read
+    // z with plain loads inside the chunk loop: data-gradient launches ran 1.3 - 2x slower) is off the epilogue's critical path
+    const uint32_t zslot = base + zbuf_off + static_cast<uint32_t>(((warp * CPW) * 32 + lane) * 80);
+    auto prefetch_z = [&](int it_, int sl) {
+      if constexpr (RS) {
+        TileCoord t_;
+        if (!tile_at<CTAS>(p, it_, N_TILE, rank, t_)) return;
+        const int gx_ = t_.x0 + px, gy_ = t_.y0 + py, gb_ = t_.b0 + pn;
+        const bool ok = gx_ < pW && gy_ < pH && gb_ < pB;
+        const int cc_ = eg + sl * kEpiGroups;
+        const __nv_bfloat16* src = p.bnb_z + (ok ? ((((size_t)t_.g * pB + gb_) * pH + gy_) * pW + gx_) * pCout + t_.n0 + cc_ * 32 : 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async16(zslot + sl * (32 * 80) + i * 16, src + i * 8, ok ? 16u : 0u);
+        cp_async_commit();
+      }
+    };
+    if constexpr (RS) {
+      if (has(F_BNB)) {
+#pragma unroll
+        for (int sl = 0; sl < CPW; ++sl) prefetch_z(0, sl);
+      }
+    }
     for (; tile_at<CTAS>(p, (int)tile_it, N_TILE, rank, tc); ++tile_it) {
       const int acc = tile_it & (NACC - 1);
       const int gx = tc.x0 + px, gy = tc.y0 + py, gb = tc.b0 + pn;
@@ -665,7 +691,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t pk[16];
         uint4 zq[4];   // (F_BNB) this pixel's 32 pre-activations z of the BatchNorm being differentiated
         if (has(F_BNB)) {
-          if (valid) {
+          if constexpr (RS) {
+            cp_async_wait_all();   // this thread's own copies (issued a tile ago)
+            const uint4* zs = reinterpret_cast<const uint4*>(sm + zbuf_off + ((warp * CPW + SLOT) * 32 + lane) * 80);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zq[i] = zs[i];
+          } else if (valid) {
             const uint4* zp = reinterpret_cast<const uint4*>(
                 p.bnb_z + ((((size_t)tc.g * pB + gb) * pH + gy) * pW + gx) * pCout + tc.n0 + cc * 32);
 #pragma unroll
@@ -685,6 +716,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (!(fmaf(bf16_lo(zw[j]), sc.x, sh.x) > 0.f)) r[2 * j] = 0u;
             if (!(fmaf(bf16_hi(zw[j]), sc.y, sh.y) > 0.f)) r[2 * j + 1] = 0u;
           }
+          // the slot's contents are in registers (and were used above): refill it for the next tile
+          if constexpr (RS) prefetch_z((int)tile_it + 1, SLOT);
         }
         if (affine) {
           float v[32];

@@ -105,6 +105,14 @@ __device__ __forceinline__ void tma_store_wait_all() {
 // generic-proxy smem writes -> visible to the async proxy (TMA store)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ cp.async (LDGSTS): per-thread asynchronous 16-byte copies
+// src_bytes = 16 copies, 0 zero-fills the destination (used for out-of-image pixels)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ named barriers
 __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

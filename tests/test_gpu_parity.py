@@ -123,8 +123,13 @@ def test_conv3x3_fused_pool_stats_head(cuda, halo):
     x5 = torch.randn(G, B, H, W, cin, device=cuda).bfloat16()
     w = torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5)
     hw, hb = torch.randn(2, cout, device=cuda) * 0.2, torch.randn(2, device=cuda)
-    res = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), cout, None, None, relu=False, pool=True, stats=True,
+    # eval-style epilogue options (pool + 1x1 head) in one launch; the BatchNorm moments come from the training
+    # instantiation (raw-accumulator epilogue, sums accumulated in registers) in a second launch of the same conv
+    res = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), cout, None, None, relu=False, pool=True,
                       head=(hw, hb), tune=dict(halo=halo))
+    res_t = ops.conv3x3(x5, ops.pack_conv_weight(w, 0), cout, stats=True, tune=dict(halo=halo))
+    assert torch.equal(res_t["y"], res["y"])
+    res["stats"] = res_t["stats"]
     ref = conv_ref_cpu(x5, w, None, None, False)
     refq = ref.bfloat16().float()            # the stored activation is bf16; fused consumers see the stored value
     y = res["y"].reshape(G * B, H, W, cout).permute(0, 3, 1, 2).float().cpu()
@@ -170,7 +175,7 @@ def test_conv3x3_fused_date_product(cuda, H, W, cin, cout, tune):
     wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=cuda) / (3.0 * cin ** 0.5), 0)
     cat = torch.full((1, B, H, W, cout + 64), 7.0, device=cuda, dtype=torch.bfloat16)
     plain = ops.conv3x3(x5, wp, cout, relu=True, tune=tune)["y"]
-    fused = ops.conv3x3(x5, wp, cout, relu=True, tune=tune, prod_out=cat, pool=True, stats=True)
+    fused = ops.conv3x3(x5, wp, cout, relu=True, tune=tune, prod_out=cat, pool=True)
     assert torch.equal(fused["y"], plain)
     assert torch.equal(cat[0, ..., :cout], torch.relu(plain[0].float() * plain[1].float()).bfloat16())
     assert bool((cat[0, ..., cout:] == 7.0).all())                 # the upsample half is left untouched
