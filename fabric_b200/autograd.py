@@ -23,6 +23,8 @@ LAST_SAVED = None
 # epilogue, so BatchNorm 1's backward is ONE pass over (dy, z) instead of a reduce pass + an apply pass (False = the
 # stand-alone kernels, kept as the cross-check)
 FUSE_BN_BWD_REDUCE = True
+# the product-fused encoder activations a2 (levels inc .. down3) are not stored; BatchNorm-2's backward recomputes them from z2
+RECOMPUTE_ENCODER_ACT = True
 
 # backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
 BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")
@@ -39,7 +41,10 @@ def _dc_forward(dc, x5, pool, prod_out=None):
     a1, _ = ops.bn_apply_relu(r1["y"], s1[0], s1[1])
     r2 = ops.conv3x3(a1, dc._packed(3, training=True), dc.out_ch, stats=True, tune=dc.tune2)
     s2 = ops.bn_finalize(r2["stats"], b2, c2.bias, n, g)
-    a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out)
+    # encoder levels 1-4: the activation is consumed only through its pooled copy and the date product, and backward
+    # recomputes it from z2 (bit-identically) -- it never touches HBM.  (KEEP_SAVED: tests want to look at it.)
+    skip_a = RECOMPUTE_ENCODER_ACT and pool and prod_out is not None and not KEEP_SAVED
+    a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out, write_a=not skip_a)
     saved = dict(x=x5, z1=r1["y"], a1=a1, z2=r2["y"], a2=a2, s1=s1, s2=s2)
     return a2, pooled, saved
 
@@ -126,19 +131,19 @@ class _BiDateNetTrain(torch.autograd.Function):
             # decoder, top down: d(cat) = [d(skip product) | d(upsampled low)]
             dcat4 = _dc_backward(model.up4.conv, sv["up4"], du4, False, None, True, grads, sink)
             done("up4")
-            e1 = sv["inc"]["a2"]
+            e1 = sv["inc"]["z2"]
             du3 = ops.up_input_bwd(dcat4, e1.shape[4], e1.shape[2] // 2, e1.shape[3] // 2)
             dcat3 = _dc_backward(model.up3.conv, sv["up3"], du3, False, None, True, grads, sink)
             done("up3")
-            e2 = sv["down1"]["a2"]
+            e2 = sv["down1"]["z2"]
             du2 = ops.up_input_bwd(dcat3, e2.shape[4], e2.shape[2] // 2, e2.shape[3] // 2)
             dcat2 = _dc_backward(model.up2.conv, sv["up2"], du2, False, None, True, grads, sink)
             done("up2")
-            e3 = sv["down2"]["a2"]
+            e3 = sv["down2"]["z2"]
             du1 = ops.up_input_bwd(dcat2, e3.shape[4], e3.shape[2] // 2, e3.shape[3] // 2)
             dcat1 = _dc_backward(model.up1.conv, sv["up1"], du1, False, None, True, grads, sink)
             done("up1")
-            e4 = sv["down3"]["a2"]
+            e4 = sv["down3"]["z2"]
             dp5 = ops.up_input_bwd(dcat1, e4.shape[4], e4.shape[2] // 2, e4.shape[3] // 2)   # d relu(x5_d2 * x5_d1)
             # encoder, bottom up: each level's output gets the product-fusion gradient (times the other date's
             # activation) plus the gradient flowing back through the max pool from the level below

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restric
           m[j] = fmaxf(m[j], f[j]);
         }
         const uint4 av = pack8(f);
-        a[(size_t)((img * H + y) * W + x) * C8 + c8] = av;
+        if (a) a[(size_t)((img * H + y) * W + x) * C8 + c8] = av;
         if (prod) {
           if (gi == 0) {
             first[d] = av;
@@ -554,10 +554,23 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwd p, const flo
 // Walking the two date groups one after the other (kernels above) reads a0, a1 and ga twice per pass (8.5 tensor units of
 // HBM traffic); here one thread handles 8 channels of one pixel for BOTH dates, so z0, z1, a0, a1, ga, gp cross HBM once
 // per pass (5.25 units).  a_g > 0 is the ReLU mask (a = relu(bn(z)) as stored), so scale / shift are not needed.
-template <bool GP>
+// RECOMP: the activation tensor is not read (nor stored by the forward pass at all): a = bf16(relu(z * scale + shift)) is
+// recomputed from z exactly as bn_apply_kernel computed and rounded it, for the pixel, for the other date (product adjoint)
+// and for the 2x2 pooling window (arg-max routing).  Per pass z0, z1, ga, gp cross HBM: 3.5 tensor units instead of 5.25.
+template <bool RECOMP>
+__device__ __forceinline__ void bn_act8(const uint4& zv, const float (&sc)[8], const float (&sh)[8], float (&af)[8]) {
+  float zf[8];
+  unpack8(zv, zf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) zf[j] = fmaxf(fmaf(zf[j], sc[j], sh[j]), 0.f);
+  unpack8(pack8(zf), af);   // the value as the forward pass stored it (bf16, round to nearest even)
+}
+
+template <bool GP, bool RECOMP>
 __device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_t c8, uint32_t npix, float (&dy)[2][8],
-                                           float (&zf)[2][8]) {
+                                           float (&zf)[2][8], const float (&sc)[2][8], const float (&sh)[2][8]) {
   const uint32_t C8 = p.C >> 3;
+  const uint4* asrc = RECOMP ? p.z : p.a;   // where the pooling window is read from
   uint4 zr[2], ar[2], gpr[2], wv[2][4];
   const uint4 gar = __ldg(p.ga + (size_t)pix * p.ga_c8 + c8);
   bool pool_ok = false;
@@ -571,8 +584,8 @@ __device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_
     for (int g = 0; g < 2; ++g) {
       if (pool_ok) {
         const size_t w00 = (size_t)(g * npix + pix - (y & 1) * W - (x & 1)) * C8 + c8;
-        wv[g][0] = __ldg(p.a + w00), wv[g][1] = __ldg(p.a + w00 + C8), wv[g][2] = __ldg(p.a + w00 + (size_t)W * C8),
-        wv[g][3] = __ldg(p.a + w00 + (size_t)(W + 1) * C8);
+        wv[g][0] = __ldg(asrc + w00), wv[g][1] = __ldg(asrc + w00 + C8), wv[g][2] = __ldg(asrc + w00 + (size_t)W * C8),
+        wv[g][3] = __ldg(asrc + w00 + (size_t)(W + 1) * C8);
         gpr[g] = __ldg(p.gp + (size_t)(((g * p.B + b) * Hp + (y >> 1)) * Wp + (x >> 1)) * C8 + c8);
       }
     }
@@ -580,12 +593,17 @@ __device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     zr[g] = __ldg(p.z + (size_t)(g * npix + pix) * C8 + c8);
-    ar[g] = __ldg(p.a + (size_t)(g * npix + pix) * C8 + c8);
+    if (!RECOMP) ar[g] = __ldg(p.a + (size_t)(g * npix + pix) * C8 + c8);
   }
   float gaf[8], af[2][8];
   unpack8(gar, gaf);
-  unpack8(ar[0], af[0]);
-  unpack8(ar[1], af[1]);
+  if (RECOMP) {
+    bn_act8<true>(zr[0], sc[0], sh[0], af[0]);
+    bn_act8<true>(zr[1], sc[1], sh[1], af[1]);
+  } else {
+    unpack8(ar[0], af[0]);
+    unpack8(ar[1], af[1]);
+  }
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     unpack8(zr[g], zf[g]);
@@ -595,13 +613,15 @@ __device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_
       // nn.MaxPool2d backward: the pooled gradient goes to the FIRST maximum of the 2x2 window in scan order
       float m[8], gpv[8];
       int best[8];
-      unpack8(wv[g][0], m);
+      if (RECOMP) bn_act8<true>(wv[g][0], sc[g], sh[g], m);
+      else unpack8(wv[g][0], m);
 #pragma unroll
       for (int j = 0; j < 8; ++j) best[j] = 0;
 #pragma unroll
       for (int d = 1; d < 4; ++d) {
         float v[8];
-        unpack8(wv[g][d], v);
+        if (RECOMP) bn_act8<true>(wv[g][d], sc[g], sh[g], v);
+        else unpack8(wv[g][d], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (v[j] > m[j]) m[j] = v[j], best[j] = d;
@@ -617,23 +637,26 @@ __device__ __forceinline__ void bn_bwd2_dy(const BnBwd& p, uint32_t pix, uint32_
   }
 }
 
-template <bool GP>
-__global__ void __launch_bounds__(256, 2) bn_bwd2_reduce_kernel(BnBwd p, float* __restrict__ partial) {
+// (RECOMP keeps 32 more per-channel coefficients in registers: 128-thread blocks, three per SM -> 170 registers per thread)
+template <bool GP, bool RECOMP>
+__global__ void __launch_bounds__(RECOMP ? 128 : 256, RECOMP ? 3 : 2) bn_bwd2_reduce_kernel(BnBwd p, float* __restrict__ partial) {
   extern __shared__ float sm[];  // [blockDim][16]
   const uint32_t C8 = p.C >> 3;
   const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
   const uint32_t npix = (uint32_t)p.B * p.H * p.W;
   const uint32_t stride = gridDim.x * ppb;
-  float s1[2][8], s2[2][8], mu[2][8];
+  float s1[2][8], s2[2][8], mu[2][8], sc[2][8], sh[2][8];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     ld8f(p.mean + g * p.C + c8 * 8, mu[g]);
+    ld8f(p.scale + g * p.C + c8 * 8, sc[g]);
+    ld8f(p.shift + g * p.C + c8 * 8, sh[g]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[g][j] = s2[g][j] = 0.f;
   }
   for (uint32_t q = blockIdx.x * ppb + lane_p; q < npix; q += stride) {
     float dy[2][8], zf[2][8];
-    bn_bwd2_dy<GP>(p, q, c8, npix, dy, zf);
+    bn_bwd2_dy<GP, RECOMP>(p, q, c8, npix, dy, zf, sc, sh);
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
@@ -661,23 +684,25 @@ __global__ void __launch_bounds__(256, 2) bn_bwd2_reduce_kernel(BnBwd p, float* 
   }
 }
 
-template <bool GP>
-__global__ void __launch_bounds__(256, 2) bn_bwd2_apply_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
+template <bool GP, bool RECOMP>
+__global__ void __launch_bounds__(RECOMP ? 128 : 256, RECOMP ? 3 : 2) bn_bwd2_apply_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
   const uint32_t C8 = p.C >> 3;
   const uint32_t npix = (uint32_t)p.B * p.H * p.W;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t c8 = gtid % C8;
   const uint32_t pstride = (gridDim.x * blockDim.x) / C8;   // host guarantees divisibility
-  float k0[2][8], kz[2][8], kc[2][8];
+  float k0[2][8], kz[2][8], kc[2][8], sc[2][8], sh[2][8];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, k0[g]);
     ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kz[g]);
     ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc[g]);
+    ld8f(p.scale + g * p.C + c8 * 8, sc[g]);
+    ld8f(p.shift + g * p.C + c8 * 8, sh[g]);
   }
   for (uint32_t q = gtid / C8; q < npix; q += pstride) {
     float dy[2][8], zf[2][8];
-    bn_bwd2_dy<GP>(p, q, c8, npix, dy, zf);
+    bn_bwd2_dy<GP, RECOMP>(p, q, c8, npix, dy, zf, sc, sh);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       float r[8];
@@ -824,7 +849,8 @@ int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* sh
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  if (!z || !scale || !shift || !a) return fail(FB_ERR_ARG, "null pointer");
+  if (!z || !scale || !shift) return fail(FB_ERR_ARG, "null pointer");
+  if (!a && !(pool_out && prod_out)) return fail(FB_ERR_ARG, "the activation may be skipped only when both its pooled copy and the date product are written");
   if (C % 8) return fail(FB_ERR_SHAPE, "C must be a multiple of 8");
   if ((double)G * B * H * W * C / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   if (prod_out && (G != 2 || prod_channels < C || prod_channels % 8)) return fail(FB_ERR_SHAPE, "product fusion needs G == 2 and prod_channels >= C");
@@ -962,7 +988,9 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   if (rc) return rc;
   if (!z || !scale || !shift || !mean || !invstd || !gamma || !dz || !dgamma || !dbeta || !ws) return fail(FB_ERR_ARG, "null pointer");
   if (!ga && !gp) return fail(FB_ERR_ARG, "no gradient source");
-  if ((mul_other || gp) && !a) return fail(FB_ERR_ARG, "activation tensor needed for product / pool routing");
+  // product-fused encoder levels (both dates per thread): a == NULL means "recompute the activation from z"
+  const bool dual_ = mul_other && G == 2 && ga && ga_groups == 1;
+  if ((mul_other || gp) && !a && !dual_) return fail(FB_ERR_ARG, "activation tensor needed for product / pool routing");
   if (mul_other && G != 2) return fail(FB_ERR_SHAPE, "product fusion needs both date groups");
   if (C % 8 || 256 % (C / 8) || (ga && (ga_channels % 8 || ga_channels < C))) return fail(FB_ERR_SHAPE, "bad channels");
   if ((double)G * B * H * W * (ga ? ga_channels : C) / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
@@ -974,14 +1002,19 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
   p.premasked = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = di.sms * 2;   // = resident blocks (256 threads, 2 per SM): one balanced wave
+  // = resident blocks: one balanced wave (256 threads x 2 per SM; the recompute variants 128 threads x 3 per SM)
+  const int nblk = (dual_ && !a) ? di.sms * 3 : di.sms * 2;
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
   // product-fused encoder levels: both date groups per thread (see bn_bwd2_dy)
   const bool dual = mul_other && G == 2 && ga && ga_groups == 1;
   if (phase & 1) {
-    if (dual && gp) bn_bwd2_reduce_kernel<true><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
-    else if (dual) bn_bwd2_reduce_kernel<false><<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
+    const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 16 * sizeof(float);
+    // (the recompute variants run nblk blocks of 128 threads: the partial layout [nblk][G][C][2] is the same)
+    if (dual && gp && !a) bn_bwd2_reduce_kernel<true, true><<<nblk, 128, sm1, st>>>(p, partial);
+    else if (dual && gp) bn_bwd2_reduce_kernel<true, false><<<nblk, 256, sm2, st>>>(p, partial);
+    else if (dual && !a) bn_bwd2_reduce_kernel<false, true><<<nblk, 128, sm1, st>>>(p, partial);
+    else if (dual) bn_bwd2_reduce_kernel<false, false><<<nblk, 256, sm2, st>>>(p, partial);
     else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
     FB_CUDA(cudaGetLastError());
   }
@@ -990,8 +1023,13 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
                                                         mean, dgamma, dbeta, coef, grad_scale);
     FB_CUDA(cudaGetLastError());
     const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
-    if (dual && gp) bn_bwd2_apply_kernel<true><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
-    else if (dual) bn_bwd2_apply_kernel<false><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+    const int g2 = ew_grid(n, 256, di.sms);
+    uint4* dzo = reinterpret_cast<uint4*>(dz);
+    const int g1 = ew_grid(n, 128, di.sms);
+    if (dual && gp && !a) bn_bwd2_apply_kernel<true, true><<<g1, 128, 0, st>>>(p, coef, dzo);
+    else if (dual && gp) bn_bwd2_apply_kernel<true, false><<<g2, 256, 0, st>>>(p, coef, dzo);
+    else if (dual && !a) bn_bwd2_apply_kernel<false, true><<<g1, 128, 0, st>>>(p, coef, dzo);
+    else if (dual) bn_bwd2_apply_kernel<false, false><<<g2, 256, 0, st>>>(p, coef, dzo);
     else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
     FB_CUDA(cudaGetLastError());
   }
@@ -1046,7 +1084,7 @@ int64_t fabric_b200_bn_bwd_partial_floats(int G, int C) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  return (int64_t)di.sms * 2 * G * C * 2;
+  return (int64_t)di.sms * 3 * G * C * 2;
 }
 
 int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream) {

@@ -362,11 +362,12 @@ def bn_finalize(stats: torch.Tensor, bn: torch.nn.BatchNorm2d, conv_bias, count_
 
 
 def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, pool: bool = False,
-                  prod_out: Optional[torch.Tensor] = None):
+                  prod_out: Optional[torch.Tensor] = None, write_a: bool = True):
     """a = relu(z*scale[g]+shift[g]) (+ MaxPool2d(2) copy) (+ relu(a[1]*a[0]) into prod_out[..., :C], the skip half of the
-    decoder input [1,B,H,W,Ct])."""
+    decoder input [1,B,H,W,Ct]).  ``write_a=False`` (only with pool and prod_out): the full-resolution activation is not
+    stored at all -- its only consumers are the pooled copy and the product, and the backward pass recomputes it from z."""
     g, b, h, w, c = z5.shape
-    a = _empty_like(z5)
+    a = _empty_like(z5) if write_a else None
     pl = _empty((g, b, h // 2, w // 2, c), dtype=torch.bfloat16, device=z5.device) if pool else None
     pc = 0
     if prod_out is not None:
