@@ -74,6 +74,10 @@ SIGNATURES = {
     "fabric_b200_outconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fabric_b200_bn_finalize": (_i, [_vp, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "fabric_b200_bn_apply_relu": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_apply_relu_head": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fabric_b200_bn_head_bwd_ws_floats": (_i64, []),
+    "fabric_b200_bn_head_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                     _f, _f, _vp]),
     "fabric_b200_seg_loss_ws_floats": (_i64, [_i, _i, _i]),
     "fabric_b200_seg_loss_fwd_bwd": (_i, [_i, _f, _f, _f, _f, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "fabric_b200_seg_loss_sums_offset": (_i64, [_i, _i, _i]),

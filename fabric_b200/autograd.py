@@ -25,14 +25,17 @@ LAST_SAVED = None
 FUSE_BN_BWD_REDUCE = True
 # the product-fused encoder activations a2 (levels inc .. down3) are not stored; BatchNorm-2's backward recomputes them from z2
 RECOMPUTE_ENCODER_ACT = True
+# up4's last BatchNorm + ReLU and `outconv` run as one pass forward and two passes backward (dlogits -> dz directly)
+FUSE_HEAD = True
 
 # backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
 BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")
 
 
-def _dc_forward(dc, x5, pool, prod_out=None):
+def _dc_forward(dc, x5, pool, prod_out=None, head=None):
     """double_conv in training mode.  Returns (a2, pooled, saved).  ``prod_out``: decoder input whose skip half
-    receives relu(a2[date 1] * a2[date 0]) from the BN-apply kernel."""
+    receives relu(a2[date 1] * a2[date 0]) from the BN-apply kernel.  ``head`` = the `outconv` module: its 1x1 conv is fused
+    into the last BN-apply pass (then ``pooled`` carries the logits)."""
     c1, b1, c2, b2 = dc.conv[0], dc.conv[1], dc.conv[3], dc.conv[4]
     g, b, h, w, _ = x5.shape
     n = b * h * w
@@ -44,19 +47,29 @@ def _dc_forward(dc, x5, pool, prod_out=None):
     # encoder levels 1-4: the activation is consumed only through its pooled copy and the date product, and backward
     # recomputes it from z2 (bit-identically) -- it never touches HBM.  (KEEP_SAVED: tests want to look at it.)
     skip_a = RECOMPUTE_ENCODER_ACT and pool and prod_out is not None and not KEEP_SAVED
-    a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out, write_a=not skip_a)
+    if head is not None:
+        a2, pooled = ops.bn_apply_relu_head(r2["y"], s2[0], s2[1], head.conv.weight, head.conv.bias)
+    else:
+        a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out, write_a=not skip_a)
     saved = dict(x=x5, z1=r1["y"], a1=a1, z2=r2["y"], a2=a2, s1=s1, s2=s2)
     return a2, pooled, saved
 
 
-def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None):
+def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None, head=None):
     """Backward of one double_conv.  ga / gp: gradient sources for its output activation (see ops.bn_relu_bwd).
-    ``sink``: {parameter: gradient tensor to write into} (the data-parallel bucket views) or None."""
+    ``sink``: {parameter: gradient tensor to write into} (the data-parallel bucket views) or None.  ``head``: the `outconv`
+    module whose forward was fused behind this block -- then ``ga`` is dL/dlogits (fp32 NCHW)."""
     c1, b1, c2, b2 = dc.conv[0], dc.conv[1], dc.conv[3], dc.conv[4]
     sink = sink or {}
     need_a = mul_other or gp is not None
-    dz2, dg2, db2 = ops.bn_relu_bwd(sv["z2"], sv["a2"] if need_a else None, ga, mul_other, gp, *sv["s2"], b2.weight,
-                                    dgamma_out=sink.get(b2.weight), dbeta_out=sink.get(b2.bias))
+    if head is not None:
+        oc = head.conv
+        dz2, dg2, db2, grads[oc.weight], grads[oc.bias] = ops.bn_head_bwd(
+            ga, sv["z2"], sv["s2"], b2.weight, oc.weight, dgamma_out=sink.get(b2.weight), dbeta_out=sink.get(b2.bias),
+            dw_out=sink.get(oc.weight), db_out=sink.get(oc.bias))
+    else:
+        dz2, dg2, db2 = ops.bn_relu_bwd(sv["z2"], sv["a2"] if need_a else None, ga, mul_other, gp, *sv["s2"], b2.weight,
+                                        dgamma_out=sink.get(b2.weight), dbeta_out=sink.get(b2.bias))
     grads[c2.weight] = ops.conv3x3_wgrad(dz2, sv["a1"], dc.out_ch, out=sink.get(c2.weight))
     # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
     grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
@@ -106,8 +119,12 @@ class _BiDateNetTrain(torch.autograd.Function):
         ops.build_up_input(None, u2, out=cat3)                                          # :37
         u3, _, sv["up3"] = _dc_forward(model.up3.conv, cat3, False)
         ops.build_up_input(None, u3, out=cat4)                                          # :38
-        u4, _, sv["up4"] = _dc_forward(model.up4.conv, cat4, False)
-        logits = ops.outconv(u4, model.outc.conv.weight, model.outc.conv.bias)   # :39
+        ctx.fuse_head = FUSE_HEAD
+        if FUSE_HEAD:
+            u4, logits, sv["up4"] = _dc_forward(model.up4.conv, cat4, False, head=model.outc)   # :38-39
+        else:
+            u4, _, sv["up4"] = _dc_forward(model.up4.conv, cat4, False)
+            logits = ops.outconv(u4, model.outc.conv.weight, model.outc.conv.bias)   # :39
         ctx.model, ctx.sv, ctx.params = model, sv, params
         if KEEP_SAVED:
             global LAST_SAVED
@@ -125,11 +142,14 @@ class _BiDateNetTrain(torch.autograd.Function):
         oc = model.outc.conv
         with torch.cuda.device(dlogits.device):
             s = sink or {}
-            du4, grads[oc.weight], grads[oc.bias] = ops.outconv_bwd(dlogits, sv["up4"]["a2"], oc.weight,
-                                                                    dw_out=s.get(oc.weight), db_out=s.get(oc.bias))
+            if ctx.fuse_head:
+                # outconv's backward rides in BatchNorm-2's: dlogits -> dz2 directly, du4 is never materialised
+                dcat4 = _dc_backward(model.up4.conv, sv["up4"], dlogits, False, None, True, grads, sink, head=model.outc)
+            else:
+                du4, grads[oc.weight], grads[oc.bias] = ops.outconv_bwd(dlogits, sv["up4"]["a2"], oc.weight,
+                                                                        dw_out=s.get(oc.weight), db_out=s.get(oc.bias))
+                dcat4 = _dc_backward(model.up4.conv, sv["up4"], du4, False, None, True, grads, sink)
             done("outc")
-            # decoder, top down: d(cat) = [d(skip product) | d(upsampled low)]
-            dcat4 = _dc_backward(model.up4.conv, sv["up4"], du4, False, None, True, grads, sink)
             done("up4")
             e1 = sv["inc"]["z2"]
             du3 = ops.up_input_bwd(dcat4, e1.shape[4], e1.shape[2] // 2, e1.shape[3] // 2)

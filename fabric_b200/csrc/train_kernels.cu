@@ -126,6 +126,177 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restric
   }
 }
 
+
+// ================================================================================================ fused 1x1 head (training)
+// The last decoder BatchNorm (up4, 64 channels) and `outconv` (unet_parts.py:83-90, bidate_model.py:39) as ONE pass each way.
+// Forward: a = relu(z*scale+shift) is stored (the next step's wgrad needs nothing of it, but backward recomputes it) and the
+// logits = W a + b leave in the same pass.  One thread = 8 channels of one pixel; the 8 threads of a pixel are adjacent lanes.
+__global__ void __launch_bounds__(256) bn_apply_head_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, uint4* __restrict__ a,
+                                                            const float* __restrict__ hw, const float* __restrict__ hb,
+                                                            float* __restrict__ logits, uint32_t npix, uint32_t plane) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = gtid & 7u;
+  float sc[8], sh[8], w0[8], w1[8];
+  ld8f(scale + c8 * 8, sc);
+  ld8f(shift + c8 * 8, sh);
+  ld8f(hw + c8 * 8, w0);
+  ld8f(hw + 64 + c8 * 8, w1);
+  const float b0 = hb[0], b1 = hb[1];
+  const uint32_t pstride = (gridDim.x * blockDim.x) >> 3;
+  // (npix rounded up to the stride by the loop bound: all lanes of a pixel group stay converged for the shuffles)
+  for (uint32_t pix = gtid >> 3; pix < npix; pix += pstride) {
+    const unsigned lanes = __activemask();   // the 8 lanes of a pixel enter and leave the loop together
+    float f[8], q[8];
+    unpack8(__ldg(z + (size_t)pix * 8 + c8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    const uint4 av = pack8(f);
+    a[(size_t)pix * 8 + c8] = av;
+    unpack8(av, q);   // the head sees the activation as stored
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      l0 = fmaf(q[j], w0[j], l0);
+      l1 = fmaf(q[j], w1[j], l1);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      l0 += __shfl_xor_sync(lanes, l0, o);
+      l1 += __shfl_xor_sync(lanes, l1, o);
+    }
+    if (c8 == 0) {
+      const uint32_t b = pix / plane, o = pix - b * plane;
+      logits[(size_t)(b * 2) * plane + o] = l0 + b0;
+      logits[(size_t)(b * 2 + 1) * plane + o] = l1 + b1;
+    }
+  }
+}
+
+// Backward of the same pair: du = W^T dlogits is never materialised.  dy = relu'(.) * du;
+// pass 1: partial[blk] = { (sum dy, sum dy*xhat)[64][2], dW[2][64], db[2] };  pass 2: dz = k0*dy + kz*z + kc.
+struct HeadBwd {
+  const uint4* z;
+  const float* dlogits;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* hw;
+  uint32_t npix, plane;
+};
+constexpr int kHeadPartial = 64 * 2 + 2 * 64 + 2;
+
+__global__ void __launch_bounds__(256, 2) bn_head_bwd_reduce_kernel(HeadBwd p, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [blockDim][34]
+  const uint32_t c8 = threadIdx.x & 7u, lane_p = threadIdx.x >> 3, ppb = blockDim.x >> 3;
+  float sc[8], sh[8], mu[8], is[8], w0[8], w1[8];
+  ld8f(p.scale + c8 * 8, sc);
+  ld8f(p.shift + c8 * 8, sh);
+  ld8f(p.mean + c8 * 8, mu);
+  ld8f(p.invstd + c8 * 8, is);
+  ld8f(p.hw + c8 * 8, w0);
+  ld8f(p.hw + 64 + c8 * 8, w1);
+  float s1[8], s2[8], g0[8], g1[8], d0s = 0.f, d1s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = g0[j] = g1[j] = 0.f;
+  const uint32_t stride = gridDim.x * ppb;
+  for (uint32_t pix = blockIdx.x * ppb + lane_p; pix < p.npix; pix += stride) {
+    const uint32_t b = pix / p.plane, o = pix - b * p.plane;
+    const float d0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o), d1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+    float zf[8], af[8];
+    unpack8(__ldg(p.z + (size_t)pix * 8 + c8), zf);
+    bool on[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pre = fmaf(zf[j], sc[j], sh[j]);
+      on[j] = pre > 0.f;
+      af[j] = fmaxf(pre, 0.f);
+    }
+    float aq[8];
+    unpack8(pack8(af), aq);   // as stored by the forward pass
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dy = on[j] ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
+      s1[j] += dy;
+      s2[j] = fmaf(dy, (zf[j] - mu[j]) * is[j], s2[j]);
+      g0[j] = fmaf(d0, aq[j], g0[j]);
+      g1[j] = fmaf(d1, aq[j], g1[j]);
+    }
+    if (c8 == 0) d0s += d0, d1s += d1;
+  }
+  float* mine = sm + threadIdx.x * 34;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = s1[j], mine[8 + j] = s2[j], mine[16 + j] = g0[j], mine[24 + j] = g1[j];
+  mine[32] = d0s, mine[33] = d1s;
+  __syncthreads();
+  float* dst = partial + (size_t)blockIdx.x * kHeadPartial;
+  for (int i = threadIdx.x; i < kHeadPartial; i += blockDim.x) {
+    float s = 0.f;
+    if (i < 128) {          // (sum dy, sum dy*xhat) interleaved per channel
+      const int c = i >> 1, k = i & 1;
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * 8 + (c >> 3)) * 34 + k * 8 + (c & 7)];
+    } else if (i < 256) {   // dW[k][c]
+      const int k = (i - 128) >> 6, c = (i - 128) & 63;
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * 8 + (c >> 3)) * 34 + 16 + k * 8 + (c & 7)];
+    } else {
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * 8) * 34 + 32 + (i - 256)];
+    }
+    dst[i] = s;
+  }
+}
+
+// one block: reduce the partials, finish BatchNorm's dgamma / dbeta / coefficients and the head's dW / db
+__global__ void bn_head_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, double count, const float* __restrict__ gamma,
+                                            const float* __restrict__ invstd, const float* __restrict__ mean,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                                            float* __restrict__ dw, float* __restrict__ db, float grad_scale) {
+  for (int i = threadIdx.x; i < kHeadPartial; i += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * kHeadPartial + i];
+    if (i >= 128 && i < 256) dw[i - 128] = (float)s * grad_scale;
+    else if (i >= 256) db[i - 256] = (float)s * grad_scale;
+    else coef[3 * 64 + i] = (float)s;   // stash the sums behind the coefficients
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 64; c += blockDim.x) {
+    const double s1 = coef[3 * 64 + 2 * c], s2 = coef[3 * 64 + 2 * c + 1];
+    const float is = invstd[c], mu = mean[c];
+    const float k0 = gamma[c] * is, k1 = (float)(s1 / count), k2 = (float)(s2 / count);
+    coef[c] = k0;
+    coef[64 + c] = -k0 * is * k2;
+    coef[128 + c] = -k0 * (k1 - mu * is * k2);
+    dgamma[c] = (float)s2 * grad_scale;
+    dbeta[c] = (float)s1 * grad_scale;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_head_bwd_apply_kernel(HeadBwd p, const float* __restrict__ coef, uint4* __restrict__ dz) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = gtid & 7u;
+  float sc[8], sh[8], w0[8], w1[8], k0[8], kz[8], kc[8];
+  ld8f(p.scale + c8 * 8, sc);
+  ld8f(p.shift + c8 * 8, sh);
+  ld8f(p.hw + c8 * 8, w0);
+  ld8f(p.hw + 64 + c8 * 8, w1);
+  ld8f(coef + c8 * 8, k0);
+  ld8f(coef + 64 + c8 * 8, kz);
+  ld8f(coef + 128 + c8 * 8, kc);
+  const uint32_t pstride = (gridDim.x * blockDim.x) >> 3;
+  for (uint32_t pix = gtid >> 3; pix < p.npix; pix += pstride) {
+    const uint32_t b = pix / p.plane, o = pix - b * p.plane;
+    const float d0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o), d1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+    float zf[8], r[8];
+    unpack8(__ldg(p.z + (size_t)pix * 8 + c8), zf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dy = fmaf(zf[j], sc[j], sh[j]) > 0.f ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
+      r[j] = fmaf(k0[j], dy, fmaf(kz[j], zf[j], kc[j]));
+    }
+    dz[(size_t)pix * 8 + c8] = pack8(r);
+  }
+}
+
 // ================================================================================================ losses
 // utils/metrics.py:51-171 (dice / jaccard / tversky share one front end) and :19-48 (focal); C = 2.
 // pass 1: per block, per image column w: I_c = sum p_c t_c, P_c = sum p_c, T_c = sum t_c over the block's rows
@@ -1085,6 +1256,61 @@ int64_t fabric_b200_bn_bwd_partial_floats(int G, int C) {
   int rc = device_info(&di);
   if (rc) return rc;
   return (int64_t)di.sms * 3 * G * C * 2;
+}
+
+int fabric_b200_bn_apply_relu_head(const void* z, const float* scale, const float* shift, void* a, const float* head_w,
+                                   const float* head_b, float* logits, int B, int H, int W, int C, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!z || !scale || !shift || !a || !head_w || !head_b || !logits) return fail(FB_ERR_ARG, "null pointer");
+  if (C != 64) return fail(FB_ERR_SHAPE, "the fused head is built for 64 channels (outc = outconv(64, 2), bidate_model.py:20)");
+  if ((double)B * H * W * 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
+  const uint32_t npix = (uint32_t)B * H * W;
+  bn_apply_head_kernel<<<ew_grid((size_t)npix * 8, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(a), head_w, head_b, logits, npix, (uint32_t)H * W);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int64_t fabric_b200_bn_head_bwd_ws_floats(void) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  return (int64_t)di.sms * 2 * kHeadPartial + 3 * 64 + 128;
+}
+
+int fabric_b200_bn_head_bwd(int phase, const float* dlogits, const void* z, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, const float* gamma, const float* head_w, void* dz,
+                            float* dgamma, float* dbeta, float* dw, float* db, float* ws, int B, int H, int W, int C,
+                            float count_scale, float grad_scale, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!dlogits || !z || !scale || !shift || !mean || !invstd || !gamma || !head_w || !dz || !dgamma || !dbeta || !dw || !db || !ws)
+    return fail(FB_ERR_ARG, "null pointer");
+  if (C != 64) return fail(FB_ERR_SHAPE, "the fused head is built for 64 channels");
+  if (phase < 1 || phase > 3) return fail(FB_ERR_ARG, "phase must be 1 (reduce), 2 (finalize + apply) or 3 (both)");
+  if ((double)B * H * W * 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
+  HeadBwd p;
+  p.z = reinterpret_cast<const uint4*>(z), p.dlogits = dlogits, p.scale = scale, p.shift = shift, p.mean = mean, p.invstd = invstd;
+  p.hw = head_w, p.npix = (uint32_t)B * H * W, p.plane = (uint32_t)H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = di.sms * 2;
+  float* partial = ws;
+  float* coef = ws + (size_t)nblk * kHeadPartial;
+  if (phase & 1) {
+    bn_head_bwd_reduce_kernel<<<nblk, 256, 256 * 34 * sizeof(float), st>>>(p, partial);
+    FB_CUDA(cudaGetLastError());
+  }
+  if (phase & 2) {
+    bn_head_bwd_finalize_kernel<<<1, 256, 0, st>>>(partial, nblk, (double)B * H * W * (double)count_scale, gamma, invstd, mean,
+                                                   dgamma, dbeta, coef, dw, db, grad_scale);
+    FB_CUDA(cudaGetLastError());
+    bn_head_bwd_apply_kernel<<<ew_grid((size_t)p.npix * 8, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
+    FB_CUDA(cudaGetLastError());
+  }
+  return FB_OK;
 }
 
 int fabric_b200_up_input_bwd(const void* dcat, void* dlow, int B, int H, int W, int Cs, int h, int w, int Cl, void* stream) {

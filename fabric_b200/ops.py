@@ -379,6 +379,48 @@ def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, po
     return a, pl
 
 
+def bn_apply_relu_head(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, head_w: torch.Tensor, head_b: torch.Tensor):
+    """up4's last BatchNorm + ReLU and `outconv` in one pass: returns (a [1,B,H,W,64] bf16, logits [B,2,H,W] fp32)."""
+    _need_cuda(z5, scale, shift, head_w, head_b)
+    g, b, h, w, c = z5.shape
+    assert g == 1 and head_w.shape[0] == 2
+    a = _empty_like(z5)
+    logits = _empty((b, 2, h, w), dtype=torch.float32, device=z5.device)
+    check(_lib.load().fabric_b200_bn_apply_relu_head(_p(z5), _p(scale), _p(shift), _p(a),
+                                                     _p(head_w.detach().reshape(2, c).contiguous()), _p(head_b.detach()),
+                                                     _p(logits), b, h, w, c, _stream()), "bn_apply_relu_head")
+    _count()
+    return a, logits
+
+
+def bn_head_bwd(dlogits: torch.Tensor, z5: torch.Tensor, coef, gamma, head_w, dgamma_out=None, dbeta_out=None, dw_out=None,
+                db_out=None):
+    """backward of bn_apply_relu_head: (dz [1,B,H,W,64] bf16, dgamma, dbeta, d head weight [2,64,1,1], d head bias [2])"""
+    lib = _lib.load()
+    _need_cuda(dlogits, z5, dgamma_out, dbeta_out, dw_out, db_out)
+    g, b, h, w, c = z5.shape
+    dev = z5.device
+    ws = _empty(check(lib.fabric_b200_bn_head_bwd_ws_floats(), "bn_head_bwd ws"), dtype=torch.float32, device=dev)
+    dz = _empty_like(z5)
+    dgamma = dgamma_out if dgamma_out is not None else _empty(c, dtype=torch.float32, device=dev)
+    dbeta = dbeta_out if dbeta_out is not None else _empty(c, dtype=torch.float32, device=dev)
+    dw = dw_out if dw_out is not None else _empty((2, c, 1, 1), dtype=torch.float32, device=dev)
+    db = db_out if db_out is not None else _empty((2,), dtype=torch.float32, device=dev)
+
+    def call(phase, cs, gs):
+        check(lib.fabric_b200_bn_head_bwd(phase, _p(dlogits), _p(z5), _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]),
+                                          _p(gamma.detach()), _p(head_w.detach().reshape(2, c).contiguous()), _p(dz), _p(dgamma),
+                                          _p(dbeta), _p(dw), _p(db), _p(ws), b, h, w, c, cs, gs, _stream()), "bn_head_bwd")
+    if EXACT is not None and EXACT.world > 1:
+        call(1, 1.0, 1.0)
+        EXACT.all_reduce(ws[:sm_count() * 2 * 258])
+        call(2, float(EXACT.world), 1.0 / EXACT.world)
+    else:
+        call(3, 1.0, 1.0)
+    _count(3)
+    return dz, dgamma, dbeta, dw, db
+
+
 LOSS_KINDS = {"tversky": 0, "dice": 1, "jaccard": 2, "focal": 3, "ce": 4, "bce": 4}
 
 

@@ -168,6 +168,23 @@ int fabric_b200_bn_finalize(const float* stats_ws, int grid, int n_tile, int C, 
 int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* shift, void* a, void* pool_out, void* prod_out,
                               int prod_channels, int G, int B, int H, int W, int C, void* stream);
 
+/* The last decoder BatchNorm + ReLU (up4, 64 channels) and `outconv` (unet_parts.py:83-90, bidate_model.py:38-39) in ONE
+ * pass: a = relu(z*scale+shift) stored as bf16 [B][H][W][64] and logits = W a + b as fp32 NCHW [B][2][H][W]. */
+int fabric_b200_bn_apply_relu_head(const void* z, const float* scale, const float* shift, void* a, const float* head_w,
+                                   const float* head_b, float* logits, int B, int H, int W, int C, void* stream);
+/* ... and their backward, also fused: du = W^T dlogits is never materialised (dy = relu'(.) * du is recomputed from
+ * dlogits in both passes), the activation needed for the head's weight gradient is recomputed from z.  Phase 1: partials
+ * of (sum dy, sum dy*xhat), dW, db into the first sms*2*258 floats of ws; phase 2: dgamma, dbeta, dw [2][64], db [2] and
+ * dz = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)); phase 3 = both.  Replaces fabric_b200_outconv_bwd +
+ * fabric_b200_bn_relu_bwd for that layer (three passes over 64-channel full-resolution tensors become two over z).
+ * count_scale / grad_scale: exact-global mode, as in fabric_b200_bn_relu_bwd_phase (the caller all-reduces the phase-1
+ * partials; grad_scale = 1/world then also applies to dw / db). */
+int64_t fabric_b200_bn_head_bwd_ws_floats(void);
+int fabric_b200_bn_head_bwd(int phase, const float* dlogits, const void* z, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, const float* gamma, const float* head_w, void* dz,
+                            float* dgamma, float* dbeta, float* dw, float* db, float* ws, int B, int H, int W, int C,
+                            float count_scale, float grad_scale, void* stream);
+
 /* ---- training: losses (utils/metrics.py) --------------------------------------------------------------------- */
 
 /* kind: 0 tversky(alpha,beta) :130-171, 1 dice :51-83, 2 jaccard :86-119, 3 focal(gamma) :19-48,
