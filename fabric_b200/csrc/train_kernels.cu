@@ -144,31 +144,40 @@ __global__ void __launch_bounds__(256) bn_apply_head_kernel(const uint4* __restr
   ld8f(hw + 64 + c8 * 8, w1);
   const float b0 = hb[0], b1 = hb[1];
   const uint32_t pstride = (gridDim.x * blockDim.x) >> 3;
-  // (npix rounded up to the stride by the loop bound: all lanes of a pixel group stay converged for the shuffles)
-  for (uint32_t pix = gtid >> 3; pix < npix; pix += pstride) {
+  constexpr int NB = 4;   // pixels in flight per thread (one 16-byte load each: with a single one the kernel sat at 2.9 TB/s)
+  for (uint32_t p0 = gtid >> 3; p0 < npix; p0 += NB * pstride) {
     const unsigned lanes = __activemask();   // the 8 lanes of a pixel enter and leave the loop together
-    float f[8], q[8];
-    unpack8(__ldg(z + (size_t)pix * 8 + c8), f);
+    uint4 zr[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-    const uint4 av = pack8(f);
-    a[(size_t)pix * 8 + c8] = av;
-    unpack8(av, q);   // the head sees the activation as stored
-    float l0 = 0.f, l1 = 0.f;
+    for (int k = 0; k < NB; ++k)
+      if (p0 + k * pstride < npix) zr[k] = __ldg(z + (size_t)(p0 + k * pstride) * 8 + c8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      l0 = fmaf(q[j], w0[j], l0);
-      l1 = fmaf(q[j], w1[j], l1);
-    }
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t pix = p0 + k * pstride;
+      const bool live = pix < npix;      // uniform over the 8 lanes of a pixel; the shuffles below run for every k
+      float f[8], q[8];
+      unpack8(live ? zr[k] : make_uint4(0u, 0u, 0u, 0u), f);
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      l0 += __shfl_xor_sync(lanes, l0, o);
-      l1 += __shfl_xor_sync(lanes, l1, o);
-    }
-    if (c8 == 0) {
-      const uint32_t b = pix / plane, o = pix - b * plane;
-      logits[(size_t)(b * 2) * plane + o] = l0 + b0;
-      logits[(size_t)(b * 2 + 1) * plane + o] = l1 + b1;
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+      const uint4 av = pack8(f);
+      if (live) a[(size_t)pix * 8 + c8] = av;
+      unpack8(av, q);   // the head sees the activation as stored
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        l0 = fmaf(q[j], w0[j], l0);
+        l1 = fmaf(q[j], w1[j], l1);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        l0 += __shfl_xor_sync(lanes, l0, o);
+        l1 += __shfl_xor_sync(lanes, l1, o);
+      }
+      if (live && c8 == 0) {
+        const uint32_t b = pix / plane, o = pix - b * plane;
+        logits[(size_t)(b * 2) * plane + o] = l0 + b0;
+        logits[(size_t)(b * 2 + 1) * plane + o] = l1 + b1;
+      }
     }
   }
 }
@@ -201,29 +210,45 @@ __global__ void __launch_bounds__(256, 2) bn_head_bwd_reduce_kernel(HeadBwd p, f
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = g0[j] = g1[j] = 0.f;
   const uint32_t stride = gridDim.x * ppb;
-  for (uint32_t pix = blockIdx.x * ppb + lane_p; pix < p.npix; pix += stride) {
-    const uint32_t b = pix / p.plane, o = pix - b * p.plane;
-    const float d0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o), d1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
-    float zf[8], af[8];
-    unpack8(__ldg(p.z + (size_t)pix * 8 + c8), zf);
-    bool on[8];
+  constexpr int NB = 4;
+  for (uint32_t p0 = blockIdx.x * ppb + lane_p; p0 < p.npix; p0 += NB * stride) {
+    uint4 zr[NB];
+    float dl0[NB], dl1[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float pre = fmaf(zf[j], sc[j], sh[j]);
-      on[j] = pre > 0.f;
-      af[j] = fmaxf(pre, 0.f);
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t pix = p0 + k * stride;
+      if (pix < p.npix) {
+        const uint32_t b = pix / p.plane, o = pix - b * p.plane;
+        zr[k] = __ldg(p.z + (size_t)pix * 8 + c8);
+        dl0[k] = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
+        dl1[k] = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+      }
     }
-    float aq[8];
-    unpack8(pack8(af), aq);   // as stored by the forward pass
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dy = on[j] ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
-      s1[j] += dy;
-      s2[j] = fmaf(dy, (zf[j] - mu[j]) * is[j], s2[j]);
-      g0[j] = fmaf(d0, aq[j], g0[j]);
-      g1[j] = fmaf(d1, aq[j], g1[j]);
+    for (int k = 0; k < NB; ++k) {
+      if (p0 + k * stride >= p.npix) break;
+      const float d0 = dl0[k], d1 = dl1[k];
+      float zf[8], af[8];
+      unpack8(zr[k], zf);
+      bool on[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(zf[j], sc[j], sh[j]);
+        on[j] = pre > 0.f;
+        af[j] = fmaxf(pre, 0.f);
+      }
+      float aq[8];
+      unpack8(pack8(af), aq);   // as stored by the forward pass
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dy = on[j] ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
+        s1[j] += dy;
+        s2[j] = fmaf(dy, (zf[j] - mu[j]) * is[j], s2[j]);
+        g0[j] = fmaf(d0, aq[j], g0[j]);
+        g1[j] = fmaf(d1, aq[j], g1[j]);
+      }
+      if (c8 == 0) d0s += d0, d1s += d1;
     }
-    if (c8 == 0) d0s += d0, d1s += d1;
   }
   float* mine = sm + threadIdx.x * 34;
 #pragma unroll
@@ -283,17 +308,33 @@ __global__ void __launch_bounds__(256, 2) bn_head_bwd_apply_kernel(HeadBwd p, co
   ld8f(coef + 64 + c8 * 8, kz);
   ld8f(coef + 128 + c8 * 8, kc);
   const uint32_t pstride = (gridDim.x * blockDim.x) >> 3;
-  for (uint32_t pix = gtid >> 3; pix < p.npix; pix += pstride) {
-    const uint32_t b = pix / p.plane, o = pix - b * p.plane;
-    const float d0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o), d1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
-    float zf[8], r[8];
-    unpack8(__ldg(p.z + (size_t)pix * 8 + c8), zf);
+  constexpr int NB = 4;
+  for (uint32_t p0 = gtid >> 3; p0 < p.npix; p0 += NB * pstride) {
+    uint4 zr[NB];
+    float dl0[NB], dl1[NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dy = fmaf(zf[j], sc[j], sh[j]) > 0.f ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
-      r[j] = fmaf(k0[j], dy, fmaf(kz[j], zf[j], kc[j]));
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t pix = p0 + k * pstride;
+      if (pix < p.npix) {
+        const uint32_t b = pix / p.plane, o = pix - b * p.plane;
+        zr[k] = __ldg(p.z + (size_t)pix * 8 + c8);
+        dl0[k] = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
+        dl1[k] = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+      }
     }
-    dz[(size_t)pix * 8 + c8] = pack8(r);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t pix = p0 + k * pstride;
+      if (pix >= p.npix) break;
+      float zf[8], r[8];
+      unpack8(zr[k], zf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dy = fmaf(zf[j], sc[j], sh[j]) > 0.f ? fmaf(dl0[k], w0[j], dl1[k] * w1[j]) : 0.f;
+        r[j] = fmaf(k0[j], dy, fmaf(kz[j], zf[j], kc[j]));
+      }
+      dz[(size_t)pix * 8 + c8] = pack8(r);
+    }
   }
 }
 
@@ -884,6 +925,122 @@ __global__ void __launch_bounds__(RECOMP ? 128 : 256, RECOMP ? 3 : 2) bn_bwd2_ap
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- quad form (recompute)
+// Same arithmetic as bn_bwd2_* with the activation recomputed from z, but ONE THREAD = 8 channels of one 2x2 pixel QUAD of
+// one date: the pooling window is the thread's own four pixels, so z of each date is loaded once per quad-thread (8 + 4 + 1
+// 16-byte loads per four pixels instead of thirteen per pixel) and the activation is recomputed 8 times per quad instead of
+// 40.  (The per-pixel recompute form above ran 40 % SLOWER than reading the stored activation: issue-bound.)
+template <bool GP, bool APPLY>
+__global__ void __launch_bounds__(128, 3) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz,
+                                                          float* __restrict__ partial) {
+  extern __shared__ float sm[];  // reduce: [blockDim][16]
+  const uint32_t C8 = p.C >> 3, H = p.H, W = p.W, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+  const uint32_t npix = (uint32_t)p.B * H * W, nquad = (uint32_t)p.B * Hq * Wq;
+  const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
+  const uint32_t stride = gridDim.x * ppb;
+  for (uint32_t g = 0; g < 2; ++g) {
+    float sc[2][8], sh[2][8];   // [own, other]
+    ld8f(p.scale + g * p.C + c8 * 8, sc[0]);
+    ld8f(p.shift + g * p.C + c8 * 8, sh[0]);
+    ld8f(p.scale + (1 - g) * p.C + c8 * 8, sc[1]);
+    ld8f(p.shift + (1 - g) * p.C + c8 * 8, sh[1]);
+    float ka[8], kb[8], kc[8];  // reduce: ka = mean, s1 / s2 in kb / kc;  apply: k0, kz, kc
+    if (APPLY) {
+      ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, ka);
+      ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kb);
+      ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc);
+    } else {
+      ld8f(p.mean + g * p.C + c8 * 8, ka);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kb[j] = kc[j] = 0.f;
+    }
+    for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
+      const uint32_t qx = q % Wq, t = q / Wq, qy = t % Hq, b = t / Hq;
+      uint4 zo[4], zt[4], gq[4], gpv;
+      bool ok[4];
+      uint32_t pix[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+        ok[d] = y < H && x < W;
+        pix[d] = (b * H + y) * W + x;
+        if (ok[d]) {
+          zo[d] = __ldg(p.z + (size_t)(g * npix + pix[d]) * C8 + c8);
+          zt[d] = __ldg(p.z + (size_t)((1 - g) * npix + pix[d]) * C8 + c8);
+          gq[d] = __ldg(p.ga + (size_t)pix[d] * p.ga_c8 + c8);
+        }
+      }
+      const bool pool_ok = GP && qy < Hp && qx < Wp;
+      if (pool_ok) gpv = __ldg(p.gp + (size_t)(((g * p.B + b) * Hp + qy) * Wp + qx) * C8 + c8);
+      // own activations of the window (as the forward pass stored them) and the arg-max of nn.MaxPool2d (first maximum in
+      // scan order); a full window exists whenever pool_ok
+      float m[8];
+      int best[8];
+      uint4 ao[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (!ok[d]) continue;
+        float af[8];
+        bn_act8<true>(zo[d], sc[0], sh[0], af);
+        ao[d] = pack8(af);
+        if (GP) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (d == 0) m[j] = af[j], best[j] = 0;
+            else if (af[j] > m[j]) m[j] = af[j], best[j] = d;
+          }
+        }
+      }
+      float gpf[8];
+      if (pool_ok) unpack8(gpv, gpf);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (!ok[d]) continue;
+        float at[8], af[8], gaf[8], zf[8], dy[8];
+        bn_act8<true>(zt[d], sc[1], sh[1], at);
+        unpack8(ao[d], af);
+        unpack8(gq[d], gaf);
+        unpack8(zo[d], zf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = gaf[j] * at[j];
+          if (pool_ok && best[j] == d) v += gpf[j];
+          dy[j] = af[j] > 0.f ? v : 0.f;
+        }
+        if (APPLY) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(ka[j], dy[j], fmaf(kb[j], zf[j], kc[j]));
+          dz[(size_t)(g * npix + pix[d]) * C8 + c8] = pack8(r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            kb[j] += dy[j];
+            kc[j] = fmaf(dy[j], zf[j] - ka[j], kc[j]);   // x invstd once, below
+          }
+        }
+      }
+    }
+    if (!APPLY) {
+      float is[8];
+      ld8f(p.invstd + g * p.C + c8 * 8, is);
+      __syncthreads();
+      float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[j] = kb[j], mine[8 + j] = kc[j] * is[j];
+      __syncthreads();
+      float* dst = partial + ((size_t)blockIdx.x * p.G + g) * p.C * 2;
+      for (int i = threadIdx.x; i < p.C * 2; i += blockDim.x) {
+        const int c = i >> 1, k = i & 1;
+        float s_ = 0.f;
+        for (uint32_t l = 0; l < ppb; ++l) s_ += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
+        dst[i] = s_;
+      }
+    }
+  }
+}
+
 // ================================================================================================ decoder-input adjoint
 // dlow[b][i][j][c] = sum_{u,v} wy(u,i) wx(v,j) dcat[b][u+padT][v+padL][Cs+c]   (adjoint of bilinear x2 + pad)
 __global__ void __launch_bounds__(256, 4)
@@ -1182,9 +1339,9 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   if (phase & 1) {
     const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 16 * sizeof(float);
     // (the recompute variants run nblk blocks of 128 threads: the partial layout [nblk][G][C][2] is the same)
-    if (dual && gp && !a) bn_bwd2_reduce_kernel<true, true><<<nblk, 128, sm1, st>>>(p, partial);
+    if (dual && gp && !a) bn_bwd2q_kernel<true, false><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual && gp) bn_bwd2_reduce_kernel<true, false><<<nblk, 256, sm2, st>>>(p, partial);
-    else if (dual && !a) bn_bwd2_reduce_kernel<false, true><<<nblk, 128, sm1, st>>>(p, partial);
+    else if (dual && !a) bn_bwd2q_kernel<false, false><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual) bn_bwd2_reduce_kernel<false, false><<<nblk, 256, sm2, st>>>(p, partial);
     else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
     FB_CUDA(cudaGetLastError());
@@ -1196,10 +1353,11 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
     const int g2 = ew_grid(n, 256, di.sms);
     uint4* dzo = reinterpret_cast<uint4*>(dz);
-    const int g1 = ew_grid(n, 128, di.sms);
-    if (dual && gp && !a) bn_bwd2_apply_kernel<true, true><<<g1, 128, 0, st>>>(p, coef, dzo);
+    const size_t nq = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);   // quad-threads per date
+    const int g1 = ew_grid(nq, 128, di.sms);
+    if (dual && gp && !a) bn_bwd2q_kernel<true, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual && gp) bn_bwd2_apply_kernel<true, false><<<g2, 256, 0, st>>>(p, coef, dzo);
-    else if (dual && !a) bn_bwd2_apply_kernel<false, true><<<g1, 128, 0, st>>>(p, coef, dzo);
+    else if (dual && !a) bn_bwd2q_kernel<false, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual) bn_bwd2_apply_kernel<false, false><<<g2, 256, 0, st>>>(p, coef, dzo);
     else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
     FB_CUDA(cudaGetLastError());
