@@ -927,81 +927,96 @@ __global__ void __launch_bounds__(RECOMP ? 128 : 256, RECOMP ? 3 : 2) bn_bwd2_ap
 
 
 // ---------------------------------------------------------------------------------------------- quad form (recompute)
-// Same arithmetic as bn_bwd2_* with the activation recomputed from z, but ONE THREAD = 8 channels of one 2x2 pixel QUAD of
-// one date: the pooling window is the thread's own four pixels, so z of each date is loaded once per quad-thread (8 + 4 + 1
-// 16-byte loads per four pixels instead of thirteen per pixel) and the activation is recomputed 8 times per quad instead of
-// 40.  (The per-pixel recompute form above ran 40 % SLOWER than reading the stored activation: issue-bound.)
+// Same arithmetic as bn_bwd2_* with the activation recomputed from z, but ONE THREAD = 8 channels of one 2x2 pixel QUAD, for
+// BOTH dates: the pooling window is the thread's own four pixels, so z0, z1, ga and gp cross HBM exactly once per pass (3.5
+// tensor units, against 5.25 for the kernels reading the stored activation) with 8 + 4 + 2 sixteen-byte loads in flight per
+// thread, and the activation is recomputed 8 times per quad.  (A per-pixel recompute form -- every thread re-reading and
+// re-computing its whole window -- ran 40 % SLOWER than reading the stored activation: issue-bound.  A per-date quad form
+// read z twice.)
 template <bool GP, bool APPLY>
-__global__ void __launch_bounds__(128, 3) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz,
+__global__ void __launch_bounds__(128, 2) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz,
                                                           float* __restrict__ partial) {
   extern __shared__ float sm[];  // reduce: [blockDim][16]
   const uint32_t C8 = p.C >> 3, H = p.H, W = p.W, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
   const uint32_t npix = (uint32_t)p.B * H * W, nquad = (uint32_t)p.B * Hq * Wq;
   const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
   const uint32_t stride = gridDim.x * ppb;
-  for (uint32_t g = 0; g < 2; ++g) {
-    float sc[2][8], sh[2][8];   // [own, other]
-    ld8f(p.scale + g * p.C + c8 * 8, sc[0]);
-    ld8f(p.shift + g * p.C + c8 * 8, sh[0]);
-    ld8f(p.scale + (1 - g) * p.C + c8 * 8, sc[1]);
-    ld8f(p.shift + (1 - g) * p.C + c8 * 8, sh[1]);
-    float ka[8], kb[8], kc[8];  // reduce: ka = mean, s1 / s2 in kb / kc;  apply: k0, kz, kc
+  float sc[2][8], sh[2][8];
+  float ka[2][8], kb[2][8], kc[2][8];  // reduce: ka = mean, sums s1 / s2 in kb / kc;  apply: k0, kz, kc
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    ld8f(p.scale + g * p.C + c8 * 8, sc[g]);
+    ld8f(p.shift + g * p.C + c8 * 8, sh[g]);
     if (APPLY) {
-      ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, ka);
-      ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kb);
-      ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc);
+      ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, ka[g]);
+      ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kb[g]);
+      ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc[g]);
     } else {
-      ld8f(p.mean + g * p.C + c8 * 8, ka);
+      ld8f(p.mean + g * p.C + c8 * 8, ka[g]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) kb[j] = kc[j] = 0.f;
+      for (int j = 0; j < 8; ++j) kb[g][j] = kc[g][j] = 0.f;
     }
-    for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
-      const uint32_t qx = q % Wq, t = q / Wq, qy = t % Hq, b = t / Hq;
-      uint4 zo[4], zt[4], gq[4], gpv;
-      bool ok[4];
-      uint32_t pix[4];
+  }
+  for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
+    const uint32_t qx = q % Wq, t = q / Wq, qy = t % Hq, b = t / Hq;
+    uint4 zv[2][4], gq[4], gpv[2];
+    bool ok[4];
+    uint32_t pix[4];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-        ok[d] = y < H && x < W;
-        pix[d] = (b * H + y) * W + x;
+    for (int d = 0; d < 4; ++d) {
+      const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
+      ok[d] = y < H && x < W;
+      pix[d] = (b * H + y) * W + x;
+      if (ok[d]) {
+        zv[0][d] = __ldg(p.z + (size_t)pix[d] * C8 + c8);
+        zv[1][d] = __ldg(p.z + (size_t)(npix + pix[d]) * C8 + c8);
+        gq[d] = __ldg(p.ga + (size_t)pix[d] * p.ga_c8 + c8);
+      }
+    }
+    const bool pool_ok = GP && qy < Hp && qx < Wp;   // (then the whole window exists)
+    if (pool_ok) {
+      gpv[0] = __ldg(p.gp + (size_t)((b * Hp + qy) * Wp + qx) * C8 + c8);
+      gpv[1] = __ldg(p.gp + (size_t)(((p.B + b) * Hp + qy) * Wp + qx) * C8 + c8);
+    }
+    // activations of both dates as the forward pass stored them (bf16), kept packed
+    uint4 av[2][4];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
         if (ok[d]) {
-          zo[d] = __ldg(p.z + (size_t)(g * npix + pix[d]) * C8 + c8);
-          zt[d] = __ldg(p.z + (size_t)((1 - g) * npix + pix[d]) * C8 + c8);
-          gq[d] = __ldg(p.ga + (size_t)pix[d] * p.ga_c8 + c8);
+          float af[8];
+          bn_act8<true>(zv[g][d], sc[g], sh[g], af);
+          av[g][d] = pack8(af);
         }
-      }
-      const bool pool_ok = GP && qy < Hp && qx < Wp;
-      if (pool_ok) gpv = __ldg(p.gp + (size_t)(((g * p.B + b) * Hp + qy) * Wp + qx) * C8 + c8);
-      // own activations of the window (as the forward pass stored them) and the arg-max of nn.MaxPool2d (first maximum in
-      // scan order); a full window exists whenever pool_ok
-      float m[8];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      // arg-max of nn.MaxPool2d over the window: the FIRST maximum in scan order
       int best[8];
-      uint4 ao[4];
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        if (!ok[d]) continue;
-        float af[8];
-        bn_act8<true>(zo[d], sc[0], sh[0], af);
-        ao[d] = pack8(af);
-        if (GP) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (d == 0) m[j] = af[j], best[j] = 0;
-            else if (af[j] > m[j]) m[j] = af[j], best[j] = d;
-          }
-        }
-      }
       float gpf[8];
-      if (pool_ok) unpack8(gpv, gpf);
+      if (pool_ok) {
+        float m[8];
+        unpack8(av[g][0], m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = 0;
+#pragma unroll
+        for (int d = 1; d < 4; ++d) {
+          float v[8];
+          unpack8(av[g][d], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > m[j]) m[j] = v[j], best[j] = d;
+        }
+        unpack8(gpv[g], gpf);
+      }
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         if (!ok[d]) continue;
         float at[8], af[8], gaf[8], zf[8], dy[8];
-        bn_act8<true>(zt[d], sc[1], sh[1], at);
-        unpack8(ao[d], af);
+        unpack8(av[1 - g][d], at);
+        unpack8(av[g][d], af);
         unpack8(gq[d], gaf);
-        unpack8(zo[d], zf);
+        unpack8(zv[g][d], zf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = gaf[j] * at[j];
@@ -1011,24 +1026,27 @@ __global__ void __launch_bounds__(128, 3) bn_bwd2q_kernel(BnBwd p, const float* 
         if (APPLY) {
           float r[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaf(ka[j], dy[j], fmaf(kb[j], zf[j], kc[j]));
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(ka[g][j], dy[j], fmaf(kb[g][j], zf[j], kc[g][j]));
           dz[(size_t)(g * npix + pix[d]) * C8 + c8] = pack8(r);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            kb[j] += dy[j];
-            kc[j] = fmaf(dy[j], zf[j] - ka[j], kc[j]);   // x invstd once, below
+            kb[g][j] += dy[j];
+            kc[g][j] = fmaf(dy[j], zf[j] - ka[g][j], kc[g][j]);   // x invstd once, below
           }
         }
       }
     }
-    if (!APPLY) {
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
       float is[8];
       ld8f(p.invstd + g * p.C + c8 * 8, is);
       __syncthreads();
       float* mine = sm + threadIdx.x * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mine[j] = kb[j], mine[8 + j] = kc[j] * is[j];
+      for (int j = 0; j < 8; ++j) mine[j] = kb[g][j], mine[8 + j] = kc[g][j] * is[j];
       __syncthreads();
       float* dst = partial + ((size_t)blockIdx.x * p.G + g) * p.C * 2;
       for (int i = threadIdx.x; i < p.C * 2; i += blockDim.x) {
@@ -1330,8 +1348,8 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
   p.premasked = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  // = resident blocks: one balanced wave (256 threads x 2 per SM; the recompute variants 128 threads x 3 per SM)
-  const int nblk = (dual_ && !a) ? di.sms * 3 : di.sms * 2;
+  // = resident blocks: one balanced wave (256 threads x 2 per SM; the recompute quad kernels 128 threads x 2 per SM)
+  const int nblk = di.sms * 2;
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
   // product-fused encoder levels: both date groups per thread (see bn_bwd2_dy)
