@@ -23,6 +23,7 @@ LAST_SAVED = None
 # epilogue, so BatchNorm 1's backward is ONE pass over (dy, z) instead of a reduce pass + an apply pass (False = the
 # stand-alone kernels, kept as the cross-check)
 FUSE_BN_BWD_REDUCE = True
+FUSE_BN_BWD_MAX_CH = 64
 # the product-fused encoder activations a2 (levels inc .. down3) are not stored; BatchNorm-2's backward recomputes them from z2
 RECOMPUTE_ENCODER_ACT = True
 # up4's last BatchNorm + ReLU and `outconv` run as one pass forward and two passes backward (dlogits -> dz directly)
@@ -74,9 +75,10 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None, head=None
     # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
     grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
     grads[b2.weight], grads[b2.bias] = dg2, db2
-    # (fused for the 64- and 128-wide layers -- the big tensors; on the 256-wide tiles the epilogue reads z with plain
-    #  loads and the fusion measured slower than the stand-alone reduce pass over those small maps)
-    if FUSE_BN_BWD_REDUCE and dc.out_ch <= 128:
+    # (fused for the 64-wide layers -- the 256 x 256 and 128 x 128 tensors, where the stand-alone reduce costs most.  The
+    #  128-wide data gradients keep their weight slab resident only without the prefetch buffer, and measured faster with the
+    #  stand-alone reduce pass (0.38 + 0.2 ms against 0.66 ms); on the 256-wide tiles the fused form reads z with plain loads.)
+    if FUSE_BN_BWD_REDUCE and dc.out_ch <= FUSE_BN_BWD_MAX_CH:
         r = ops.conv3x3(dz2, dc._packed_dgrad(3), dc.out_ch, tag="dgrad", bnbwd=(sv["z1"], sv["s1"]))
         del dz2
         dz1, dg1, db1 = ops.bn_bwd_from_partials(sv["z1"], r["y"], r["stats"], sv["s1"], b1.weight,

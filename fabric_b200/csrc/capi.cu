@@ -118,7 +118,7 @@ int plan_conv_on(const fb_conv3x3_desc* d, ConvPlan* pl, const DeviceInfo& di) {
   const int pool_tma = (d->pool_out && p.bh == 16) ? 1 : 0;
   const int prod_tma = (d->prod_out && out_bufs == 2 && !d->store_main) ? 1 : 0;
   const int fixed = out_bufs * 128 * n_tile * 2 + (pool_tma ? out_bufs * 4 * (n_tile / 64) * 1024 : 0) +
-                    fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr, d->bnbwd_z != nullptr) +
+                    fb::conv_misc_bytes(n_tile, d->stats_ws != nullptr && !rs, d->bnbwd_z != nullptr) +
                     ((rs && d->bnbwd_z) ? fb::conv_zbuf_bytes(n_tile, ew) : 0) + 1024;
   const int avail = smem_cap - fixed;
   const int kblocks = 9 * p.kchunks;

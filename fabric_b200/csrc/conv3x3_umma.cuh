@@ -41,7 +41,7 @@ struct Conv3x3Params {
   float* stats_out;         // nullable: per-CTA BN moment partials [grid][2][N_TILE][2] (sum, sum of squares)
   // fused BatchNorm-backward reduce (data-gradient launches): the conv output is dL/da of the BatchNorm+ReLU whose
   // pre-activation z is `bnb_z`; the epilogue applies the ReLU mask (z*scale+shift > 0), stores dy = mask * acc, and writes
-  // (sum dy, sum dy * xhat) partials into stats_out instead of the moments.  bnb_coef: fp32 [4][G][Cout] = scale, shift,
+  // (sum dy, sum dy * z) partials into stats_out instead of the moments.  bnb_coef: fp32 [4][G][Cout] = scale, shift,
   // mean, invstd of that BatchNorm.
   const __nv_bfloat16* bnb_z;
   const float* bnb_coef;
@@ -233,7 +233,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t pool_off = out_off + p.out_bufs * OUT_BYTES;
   const uint32_t ss_off = pool_off + (p.pool_tma ? p.out_bufs * POOL_BYTES : 0);
   const uint32_t st_off = ss_off + (2 * N_TILE + 136 + 256) * 4;
-  const uint32_t bnb_off = st_off + (p.stats_out ? conv_stats_bytes(N_TILE) : 0);
+  const uint32_t bnb_off = st_off + ((p.stats_out && !RS) ? conv_stats_bytes(N_TILE) : 0);   // (RS: the sums are handed over through the output staging buffer)
   const uint32_t zbuf_off = bnb_off + (p.bnb_z ? conv_bnb_bytes(N_TILE) : 0);
   const uint32_t bar_off = zbuf_off + ((RS && p.bnb_z) ? conv_zbuf_bytes(N_TILE, EW) : 0);
 
@@ -509,8 +509,18 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int m = q * 32 + lane;        // pixel row of the tile
     const int etid = threadIdx.x;       // epilogue warps come first
     float* my_stats = stats + q * (2 * N_TILE * 2);
-    if (p.stats_out)   // (the slabs exist only then)
-      for (int i = etid; i < 4 * 2 * N_TILE * 2; i += kEpiThreads) stats[i] = 0.f;
+    if (p.stats_out) {
+      if constexpr (RS) {
+        // this CTA's slot of the global partial array starts at zero: each date group adds its sums once (flush_acc)
+        const int slot_ = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+        const int pidx_ = CTAS == 2 ? (slot_ / p.num_n_tiles) * (2 * p.num_n_tiles) + rank * p.num_n_tiles + slot_ % p.num_n_tiles
+                                    : slot_;
+        float* dst_ = p.stats_out + (size_t)pidx_ * (2 * N_TILE * 2);
+        for (int i = etid; i < 2 * N_TILE * 2; i += kEpiThreads) dst_[i] = 0.f;
+      } else {
+        for (int i = etid; i < 4 * 2 * N_TILE * 2; i += kEpiThreads) stats[i] = 0.f;   // (the slabs exist only then)
+      }
+    }
     if (p.head_out) {
       for (int i = etid; i < 128; i += kEpiThreads) ss[2 * N_TILE + i] = p.head_w[i];
       if (etid < 2) ss[2 * N_TILE + 128 + etid] = p.head_b[etid];
@@ -545,18 +555,36 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int j = 0; j < AW; ++j) acc1[a_][j] = acc2[a_][j] = 0.f;
     int acc_g = -1;
+    // Hand the register sums of date group g_ over to the CTA's global partial slot.  Every epilogue warp walks the same tile
+    // sequence, so all of them arrive here at the same tile index (at most three times per kernel): the four lane quarters are
+    // summed through the output staging buffer (free once the warps' TMA stores have read it) -- no dedicated shared memory,
+    // which is what lets the 128 -> 128 training convolutions keep their 147 KB weight slab resident like the plain launch.
     auto flush_acc = [&](int g_) {
       if constexpr (REGSTATS) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        bar_sync(1, kEpiThreads);
+        float* slab = reinterpret_cast<float*>(sm + out_off);   // [4 quarters][N_TILE][2]
 #pragma unroll
         for (int sl = 0; sl < CPW; ++sl) {
           const int cc = eg + sl * kEpiGroups;
           const float c1 = colsum_finish<AW>(acc1[sl], lane), c2 = colsum_finish<AW>(acc2[sl], lane);
-          float* dst = my_stats + (g_ * N_TILE + cc * 32 + lane) * 2;
-          dst[0] += c1;
-          dst[1] += c2;
+          *reinterpret_cast<float2*>(slab + ((q * N_TILE) + cc * 32 + lane) * 2) = make_float2(c1, c2);
 #pragma unroll
           for (int j = 0; j < AW; ++j) acc1[sl][j] = acc2[sl][j] = 0.f;
         }
+        bar_sync(1, kEpiThreads);
+        const int slot_ = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+        const int pidx_ = CTAS == 2 ? (slot_ / p.num_n_tiles) * (2 * p.num_n_tiles) + rank * p.num_n_tiles + slot_ % p.num_n_tiles
+                                    : slot_;
+        float* dst_ = p.stats_out + (size_t)pidx_ * (2 * N_TILE * 2) + (size_t)g_ * N_TILE * 2;
+        for (int i = etid; i < N_TILE * 2; i += kEpiThreads) {
+          float s_ = 0.f;
+#pragma unroll
+          for (int w_ = 0; w_ < 4; ++w_) s_ += slab[w_ * (N_TILE * 2) + i];
+          dst_[i] += s_;
+        }
+        bar_sync(1, kEpiThreads);   // the slab is read; the staging buffer may be written again
       }
     };
     // epilogue options as ONE opaque register: the chunk loop tests bits instead of re-reading kernel parameters through
@@ -764,15 +792,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           };
           auto mul_w = [&](float (&v)[32]) {   // v <- v * (x or xhat)
             if (has(F_BNB)) {
-              const float* cf = bnb + (tc.g * 4 + 2) * N_TILE + cc * 32;   // mean, then invstd
+              // raw second sum: sum dy * z; the finalize kernel turns it into sum dy * xhat = invstd * (sum dy*z - mean * sum dy)
+              // in double precision (no per-channel mean / invstd loads in this loop)
               const uint32_t zw[16] = {zq[0].x, zq[0].y, zq[0].z, zq[0].w, zq[1].x, zq[1].y, zq[1].z, zq[1].w,
                                        zq[2].x, zq[2].y, zq[2].z, zq[2].w, zq[3].x, zq[3].y, zq[3].z, zq[3].w};
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float2 mu = *reinterpret_cast<const float2*>(cf + 2 * j);
-                const float2 is = *reinterpret_cast<const float2*>(cf + N_TILE + 2 * j);
-                v[2 * j] *= (bf16_lo(zw[j]) - mu.x) * is.x;
-                v[2 * j + 1] *= (bf16_hi(zw[j]) - mu.y) * is.y;
+                v[2 * j] *= bf16_lo(zw[j]);
+                v[2 * j + 1] *= bf16_hi(zw[j]);
               }
             } else {
 #pragma unroll
@@ -938,7 +965,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if constexpr (REGSTATS) {
       if (acc_g >= 0) flush_acc(acc_g);
     }
-    if (p.stats_out) {
+    if (p.stats_out && !RS) {
       bar_sync(1, kEpiThreads);
       // partial index i with i % num_n_tiles == this CTA's N tile (what bn_finalize assumes): a pair's two CTAs sit
       // num_n_tiles apart

@@ -696,6 +696,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
         s1 += v.x;
         s2 += v.y;
       }
+      // the conv epilogue accumulates the RAW second sum (sum dy * z); every lane applies the same linear map to its share
+      s2 = (s2 - (double)mean[g * C + c] * s1) * (double)invstd[g * C + c];
     } else
     for (int b = lane; b < nblk; b += 32) {
       const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * G + g) * C + c) * 2);

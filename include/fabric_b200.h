@@ -105,7 +105,7 @@ typedef struct {
   /* Fused BatchNorm-backward reduce, for the data-gradient launch whose output is dL/da of a training-mode
    * BatchNorm2d + ReLU (unet_parts.py:14-15 as seen by autograd): bnbwd_z = that layer's pre-activation z, bf16
    * [G][B][H][W][Cout]; bnbwd_coef = fp32 [4][G][Cout] (scale, shift, mean, invstd from fabric_b200_bn_finalize).  The
-   * epilogue stores dy = relu'(z*scale+shift) * acc instead of acc and writes per-CTA (sum dy, sum dy*xhat) partials into
+   * epilogue stores dy = relu'(z*scale+shift) * acc instead of acc and writes per-CTA (sum dy, sum dy*z) partials into
    * stats_ws (same layout and size as the moment partials), which fabric_b200_bn_bwd_from_partials finishes -- the
    * stand-alone reduce pass over (dL/da, z) disappears.  Raw-accumulator epilogue only (no scale / shift / relu / pool /
    * head / product). */
@@ -236,7 +236,7 @@ int fabric_b200_bn_relu_bwd_phase(int phase, const void* z, const void* a, const
                                   int G, int B, int H, int W, int C, float count_scale, float grad_scale, void* stream);
 
 /* BatchNorm(train) + ReLU backward when the producer of dL/da already did the reduce: `dy` = relu'(.) * dL/da (bf16) and
- * `partial` = per-CTA (sum dy, sum dy*xhat) in the conv epilogue's layout [grid][2][n_tile][2], both written by the
+ * `partial` = per-CTA (sum dy, sum dy*z) in the conv epilogue's layout [grid][2][n_tile][2], both written by the
  * data-gradient launch of fabric_b200_conv3x3 with bnbwd_z set.  Finishes dgamma / dbeta and writes
  * dz = gamma*invstd * (dy - mean(dy) - xhat*mean(dy*xhat)) in ONE pass over (dy, z).  coef_ws: G*3*C floats.
  * count_scale / grad_scale as in fabric_b200_bn_relu_bwd_phase (exact-global mode all-reduces `partial` first). */
