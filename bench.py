@@ -501,7 +501,8 @@ def main():
         from fabric_b200.metrics import TverskyLoss
         model.train()
         criterion = TverskyLoss(alpha=0.1, beta=0.9)                  # metadata.json:42-44
-        dp = DataParallelStep(model)                                  # owns the flat gradient bucket (+ fused SGD)
+        # owns the flat gradient bucket (+ fused SGD); FABRIC_B200_NO_OVERLAP=1: one all-reduce after backward (A/B switch)
+        dp = DataParallelStep(model, overlap=os.environ.get("FABRIC_B200_NO_OVERLAP", "0") != "1")
         dp.broadcast_parameters(0)
 
         def step(a=x1, b=x2, lab=labels):                            # train.py:88-95
