@@ -345,7 +345,10 @@ def small_shape_record(dev, steps=30):
     from fabric_b200.metrics import TverskyLoss
     out = {}
     crit = TverskyLoss(alpha=0.1, beta=0.9)
-    for name, b, s_ in (("config1_2x13x32x32", 2, 32), ("reference_default_32x13x90x90", 32, 90)):
+    for name, b, s_ in (("config1_2x13x32x32", 2, 32), ("reference_default_32x13x90x90", 32, 90),
+                        ("benchmark_64x13x256x256", PAIRS, SIZE)):
+        if b == PAIRS:
+            steps = 8
         try:
             torch.manual_seed(0)
             model = BiDateNet(13, 2).to(dev).train()
@@ -550,6 +553,23 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if os.environ.get("FABRIC_B200_PROFILE_STEP"):
+        # profiling hook (never a bench number): exactly ONE step between cudaProfilerStart / Stop, for
+        # `ncu --profile-from-start off --set full` (tools/prof_round2.sh); "infer" profiles one eval forward instead
+        what = os.environ["FABRIC_B200_PROFILE_STEP"]
+        if what == "infer" and train:
+            model.eval()
+            for _ in range(2):
+                infer_step()
+        barrier()
+        torch.cuda.cudart().cudaProfilerStart()
+        infer_step() if what == "infer" else step()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profiled": what, "note": "one step under the profiler; not a benchmark"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if rank == 0:
         sampler.start()
     total_ms, launches = timed(step, args.steps, 0)

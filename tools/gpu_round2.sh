@@ -34,6 +34,8 @@ launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_bench_train.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-library --no-scene --no-infer --no-small --e2e-steps 1 > $O/${TAG}_launches_train.log 2>&1
   python tools/summarize_launches.py $O/${TAG}_launches_bench_train.csv > $O/${TAG}_launches_train_summary.md 2>&1; head -40 $O/${TAG}_launches_train_summary.md ;;
+prof)
+  bash tools/prof_round2.sh $TAG ;;
 smoke)
   echo "== smoke"
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 ;;
