@@ -581,10 +581,13 @@ def main():
     # ---- roofline of the dominant kernels (tcgen05 convolutions: forward, data-gradient and weight-gradient launches)
     conv_ms, conv_flops, layers, kinds = summarise_profile(prof, args.steps)
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    if os.path.exists(tp) and train:
+        tj = json.load(open(tp))
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_note = {"dram_bytes_per_step": tj.get("dram_bytes_per_step"), "launches_per_step": tj.get("launches_per_step"),
+                        "algorithmic_bytes_per_step": tj.get("algorithmic_bytes_per_step"), "source": tj.get("source")}
     conv_share = conv_ms / prof_total_ms
     roofline = {"bound": "tensor",
                 "kernel": "conv3x3_umma_kernel (forward" + (" + data-gradient launches) + wgrad_umma_kernel" if train else " launches)") +
@@ -596,7 +599,7 @@ def main():
                 "conv_share_of_step": conv_share, "non_conv_share_of_step": 1.0 - conv_share,
                 "non_conv": "BatchNorm statistics / apply / backward passes, loss, 1x1 head, upsample + adjoint, packing, SGD"
                             if train else "input packing, decoder upsample",
-                "by_kind": kinds, "traffic": traffic,
+                "by_kind": kinds, "traffic": traffic, "traffic_detail": traffic_note,
                 "whole_step_tflops": (TRAIN_GFLOP_PER_PAIR if train else FWD_GFLOP_PER_PAIR) * PAIRS / ms_step,
                 "whole_step_frac": (TRAIN_GFLOP_PER_PAIR if train else FWD_GFLOP_PER_PAIR) * PAIRS / ms_step / peaks["tflops"],
                 "timing": "CUDA events around each conv / wgrad launch in a second pass of the same K steps, right after the "

@@ -291,9 +291,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything arrives on them
-  // (CTAS == 2: barrier.cluster already orders the allocator's shared-memory write of the TMEM address before the reads
-  //  below; compute-sanitizer's racecheck does not model it as a CTA barrier and reported that one pattern, 147 times,
-  //  as a hazard -- profiles/r02_sanitizer.md -- so the CTA barrier is executed as well: once per kernel, free)
+  // (plus the CTA barrier for CTAS == 2 as well: barrier.cluster already orders the allocator's shared-memory write of the
+  //  TMEM address before the reads below; the CTA barrier is redundant, free, and keeps the intra-CTA ordering explicit.
+  //  compute-sanitizer racecheck still reports ONE pattern on the pair kernels only -- the peer CTA's half of the collective
+  //  tcgen05.alloc.cta_group::2 writing this CTA's result slot "racing" with this CTA's own alloc instruction -- which is
+  //  internal to that instruction: profiles/r02_sanitizer.md)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;

@@ -56,7 +56,13 @@ def test_losses_match_oracle(cuda, kind, nd):
     loss2, dl2 = ops.seg_loss_fwd_bwd(kind, dev_logits, dev_lab, 0.1, 0.9, 2.0, 1e-7)
     got, got2, want = float(loss), float(loss2), float(v.detach())
     assert got == got2 and torch.equal(dl, dl2), f"fused {kind} loss is not deterministic: {got!r} vs {got2!r}"
-    assert abs(got - want) <= 2e-6, f"{kind}: fused {got!r} vs oracle {want!r}"
+    # the same oracle in float64 arbitrates if the two fp32 results ever disagree (round 1 saw an unexplained one-off mismatch
+    # of the focal loss on two boxes; compute-sanitizer memcheck / initcheck / racecheck and the NaN-poison run are clean)
+    want64 = float(fn(logits.double(), lab))
+    assert abs(got - want64) <= 2e-6, f"{kind}: fused {got!r} vs fp64 oracle {want64!r} (fp32 oracle {want!r})"
+    # (the fp32 CPU oracle carries its own summation error -- its order depends on the host's SIMD width and thread count --
+    #  so it gets twice the budget; the focal loss here is ~1.06, i.e. 2e-6 is 17 fp32 ulps)
+    assert abs(got - want) <= 4e-6, f"{kind}: fused {got!r} vs fp32 oracle {want!r} (fp64 oracle {want64!r})"
     assert rel(dl.cpu(), l.grad) <= 1e-4
 
 
