@@ -538,6 +538,8 @@ def main():
     def profiled(fn, steps):
         """the SAME steps again with a CUDA-event pair around every conv / wgrad launch on the launching stream (kept out
         of the pass that yields `value`: ~40-100 event records per step perturb back-to-back launches)"""
+        from fabric_b200 import autograd
+        side, autograd.WGRAD_SIDE_STREAM = autograd.WGRAD_SIDE_STREAM, False   # one stream: clean per-kernel durations
         ops.CONV_PROFILE = []
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
@@ -546,6 +548,7 @@ def main():
         p1.record()
         barrier()
         prof, ops.CONV_PROFILE = ops.CONV_PROFILE, None
+        autograd.WGRAD_SIDE_STREAM = side
         return prof, p0.elapsed_time(p1)
 
     sampler = ClockSampler(local)

@@ -13,6 +13,8 @@ returns ``None`` for the parameters -- no gradient tensor is allocated, copied o
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -28,6 +30,36 @@ FUSE_BN_BWD_MAX_CH = 64
 RECOMPUTE_ENCODER_ACT = True
 # up4's last BatchNorm + ReLU and `outconv` run as one pass forward and two passes backward (dlogits -> dz directly)
 FUSE_HEAD = True
+# weight-gradient launches go to a side stream: wgrad(c) only needs dz and the saved conv input, while the main stream carries
+# on with the data gradient -> BatchNorm backward chain; both kinds of kernel fill the GPU, so what overlaps is each kernel's
+# tail (partly filled last wave) and the launch bubbles of the small finalize kernels in between
+WGRAD_SIDE_STREAM = os.environ.get("FABRIC_B200_WGRAD_SIDE", "1") != "0"
+_SIDE = {}
+
+
+def _wgrad(dz5, x5, cin_true, out):
+    if not WGRAD_SIDE_STREAM:
+        return ops.conv3x3_wgrad(dz5, x5, cin_true, out=out)
+    dev = dz5.device
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE.get(dev.index)
+    if side is None:
+        side = _SIDE[dev.index] = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dw = ops.conv3x3_wgrad(dz5, x5, cin_true, out=out)
+    # the caching allocator must not hand these blocks to later main-stream work while the side stream still reads them
+    dz5.record_stream(side)
+    x5.record_stream(side)
+    if out is None:
+        dw.record_stream(main)
+    return dw
+
+
+def _join_side(dev):
+    side = _SIDE.get(dev.index)
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
 
 # backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
 BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")
@@ -71,7 +103,7 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None, head=None
     else:
         dz2, dg2, db2 = ops.bn_relu_bwd(sv["z2"], sv["a2"] if need_a else None, ga, mul_other, gp, *sv["s2"], b2.weight,
                                         dgamma_out=sink.get(b2.weight), dbeta_out=sink.get(b2.bias))
-    grads[c2.weight] = ops.conv3x3_wgrad(dz2, sv["a1"], dc.out_ch, out=sink.get(c2.weight))
+    grads[c2.weight] = _wgrad(dz2, sv["a1"], dc.out_ch, sink.get(c2.weight))
     # a conv bias in front of a train-mode BN has zero gradient (the sink's slot was zeroed once and is never written)
     grads[c2.bias] = sink[c2.bias] if c2.bias in sink else torch.zeros_like(c2.bias)
     grads[b2.weight], grads[b2.bias] = dg2, db2
@@ -90,7 +122,7 @@ def _dc_backward(dc, sv, ga, mul_other, gp, need_dx, grads, sink=None, head=None
         dz1, dg1, db1 = ops.bn_relu_bwd(sv["z1"], None, da1, False, None, *sv["s1"], b1.weight,
                                         dgamma_out=sink.get(b1.weight), dbeta_out=sink.get(b1.bias))
         del da1
-    grads[c1.weight] = ops.conv3x3_wgrad(dz1, sv["x"], dc.in_ch, out=sink.get(c1.weight))
+    grads[c1.weight] = _wgrad(dz1, sv["x"], dc.in_ch, sink.get(c1.weight))
     grads[c1.bias] = sink[c1.bias] if c1.bias in sink else torch.zeros_like(c1.bias)
     grads[b1.weight], grads[b1.bias] = dg1, db1
     if not need_dx:
@@ -138,7 +170,12 @@ class _BiDateNetTrain(torch.autograd.Function):
         model, sv, params = ctx.model, ctx.sv, ctx.params
         dp = model.__dict__.get("_fb_dp")            # DataParallelStep that owns the gradients, if any
         sink = dp.sink if dp is not None else None
-        done = dp.block_done if dp is not None else (lambda name: None)
+        dev_ = dlogits.device
+
+        def done(name):          # every gradient of block `name` is written once the side stream's wgrads have joined
+            if dp is not None and dp.wants_block(name):
+                _join_side(dev_)
+                dp.block_done(name)
         grads = {}
         dlogits = dlogits.contiguous().float()
         oc = model.outc.conv
@@ -179,6 +216,7 @@ class _BiDateNetTrain(torch.autograd.Function):
             done("down1")
             _dc_backward(model.inc.conv, sv["inc"], dcat4, True, gp1, False, grads, sink)
             done("inc")
+        _join_side(dev_)
         ctx.sv = None
         if sink is not None:
             # the kernels wrote into the bucket views that ARE p.grad: nothing for torch to accumulate
@@ -218,6 +256,7 @@ class _DoubleConvTrain(torch.autograd.Function):
             ga = ops.pack_input(dy.contiguous().float(), c_pad=dc.out_ch).unsqueeze(0)
             need_dx = ctx.need_dx and dc.in_ch % 64 == 0       # the 13-band stem has no data gradient (its input is data)
             dx5 = _dc_backward(dc, sv, ga, False, None, need_dx, grads, None)
+            _join_side(dy.device)
             dx = ops.unpack_output(dx5[0])[:, :ctx.cin].contiguous() if dx5 is not None else None
         ctx.sv = None
         return (None, dx) + tuple(grads.get(p) for p in params)

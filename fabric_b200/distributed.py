@@ -122,6 +122,10 @@ class DataParallelStep:
         from .bidate_model import BiDateNet
         return isinstance(self.model, BiDateNet)
 
+    def wants_block(self, name: str) -> bool:
+        """does an all-reduce segment end with block ``name`` (and is there anyone to reduce with)?"""
+        return self.world > 1 and name in self.seg_after_block
+
     def block_done(self, name: str):
         """Called by the backward pass when every gradient of block ``name`` has been written: launches the all-reduce of
         the bucket segment that ends there (async; overlaps the rest of backward)."""
