@@ -35,6 +35,7 @@ FUSE_HEAD = True
 # tail (partly filled last wave) and the launch bubbles of the small finalize kernels in between
 WGRAD_SIDE_STREAM = os.environ.get("FABRIC_B200_WGRAD_SIDE", "1") != "0"
 _SIDE = {}
+_PENDING = {}
 
 
 def _wgrad(dz5, x5, cin_true, out):
@@ -48,11 +49,10 @@ def _wgrad(dz5, x5, cin_true, out):
     side.wait_stream(main)
     with torch.cuda.stream(side):
         dw = ops.conv3x3_wgrad(dz5, x5, cin_true, out=out)
-    # the caching allocator must not hand these blocks to later main-stream work while the side stream still reads them
-    dz5.record_stream(side)
-    x5.record_stream(side)
-    if out is None:
-        dw.record_stream(main)
+    # The caching allocator must not hand these blocks to later main-stream work while the side stream still reads them:
+    # they stay referenced until the streams join (Tensor.record_stream would do, but it defers every reuse to an event
+    # poll and measured pathological -- one run in two took 1.8x longer, the allocator falling back to cudaMalloc).
+    _PENDING.setdefault(dev.index, []).append((dz5, x5, dw))
     return dw
 
 
@@ -60,6 +60,7 @@ def _join_side(dev):
     side = _SIDE.get(dev.index)
     if side is not None:
         torch.cuda.current_stream(dev).wait_stream(side)
+    _PENDING.pop(dev.index, None)      # (freed blocks go back to the main stream's pool: ordered after the join)
 
 # backward order of the blocks (gradients of a block are complete when its _dc_backward returns)
 BACKWARD_ORDER = ("outc", "up4", "up3", "up2", "up1", "down4", "down3", "down2", "down1", "inc")

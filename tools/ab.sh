@@ -4,7 +4,7 @@
 V=$1; TAG=${2:-ab}
 O=gpurun_out; mkdir -p $O
 F="--steps 20 --warmup 5 --no-cpu-baseline --no-library --no-scene --no-infer --no-small --e2e-steps 1"
-for rep in 1 2; do for val in 0 1; do
+for rep in 1 2 3; do for val in 0 1; do
   env $V=$val timeout 600 python bench.py $F > $O/${TAG}_${V}_${val}_$rep.json 2>/dev/null
   python - $O/${TAG}_${V}_${val}_$rep.json $V $val <<'PY'
 import json,sys
