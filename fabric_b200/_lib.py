@@ -98,6 +98,7 @@ SIGNATURES = {
     "fabric_b200_conv3x3_wgrad_splits": (_i, [C.POINTER(WgradDesc)]),
     "fabric_b200_conv3x3_wgrad": (_i, [C.POINTER(WgradDesc), _vp]),
     "fabric_b200_wgrad_reduce": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "fabric_b200_wgrad_reduce_swapped": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "fabric_b200_gather_tiles": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fabric_b200_argmax_metrics": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "fabric_b200_scatter_tiles": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

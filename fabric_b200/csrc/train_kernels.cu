@@ -935,33 +935,77 @@ __global__ void __launch_bounds__(RECOMP ? 128 : 256, RECOMP ? 3 : 2) bn_bwd2_ap
 // thread, and the activation is recomputed 8 times per quad.  (A per-pixel recompute form -- every thread re-reading and
 // re-computing its whole window -- ran 40 % SLOWER than reading the stored activation: issue-bound.  A per-date quad form
 // read z twice.)
-template <bool GP, bool APPLY>
-__global__ void __launch_bounds__(128, 2) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz,
-                                                          float* __restrict__ partial) {
-  extern __shared__ float sm[];  // reduce: [blockDim][16]
-  const uint32_t C8 = p.C >> 3, H = p.H, W = p.W, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+// V = channels per thread: 8 (16-byte loads) or 4 (8-byte loads).  The 8-channel form needs ~220 registers (2 blocks of 128
+// threads per SM) and ncu showed it issue-latency-bound: 2 warps per scheduler, 3.6 cycles per issued instruction per warp,
+// 54 % issue utilisation at 2.9 TB/s (reduce) / 4.2 TB/s (apply).  The 4-channel form halves every per-thread array
+// (<= 128 registers, 4 blocks per SM): twice the warps to hide the same latencies, same bytes per warp-wide access pattern
+// (8 B x 32 lanes = two 128-byte pixels of a 64-channel tensor per load instruction).
+template <int V>
+struct QVec;
+template <>
+struct QVec<8> {
+  using type = uint4;
+};
+template <>
+struct QVec<4> {
+  using type = uint2;
+};
+__device__ __forceinline__ void unpackv(const uint4& v, float (&f)[8]) { unpack8(v, f); }
+__device__ __forceinline__ void unpackv(const uint2& v, float (&f)[4]) {
+  f[0] = fb::bf16_lo(v.x), f[1] = fb::bf16_hi(v.x), f[2] = fb::bf16_lo(v.y), f[3] = fb::bf16_hi(v.y);
+}
+__device__ __forceinline__ uint4 packv(const float (&f)[8]) { return pack8(f); }
+__device__ __forceinline__ uint2 packv(const float (&f)[4]) {
+  return make_uint2(fb::pack_bf16x2(f[0], f[1]), fb::pack_bf16x2(f[2], f[3]));
+}
+__device__ __forceinline__ void ldvf(const float* __restrict__ p, float (&v)[8]) { ld8f(p, v); }
+__device__ __forceinline__ void ldvf(const float* __restrict__ p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+}
+// the activation as the forward pass stored it: bf16(relu(z * scale + shift)), as floats
+template <int V, typename T>
+__device__ __forceinline__ void bn_actv(const T& zv, const float (&sc)[V], const float (&sh)[V], float (&af)[V]) {
+  float zf[V];
+  unpackv(zv, zf);
+#pragma unroll
+  for (int j = 0; j < V; ++j) zf[j] = fmaxf(fmaf(zf[j], sc[j], sh[j]), 0.f);
+  unpackv(packv(zf), af);
+}
+
+template <bool GP, bool APPLY, int V>
+__global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz_,
+                                                                     float* __restrict__ partial) {
+  using T = typename QVec<V>::type;
+  extern __shared__ float sm[];  // reduce: [blockDim][2 * V]
+  const T* __restrict__ Z = reinterpret_cast<const T*>(p.z);
+  const T* __restrict__ GA = reinterpret_cast<const T*>(p.ga);
+  const T* __restrict__ GPP = reinterpret_cast<const T*>(p.gp);
+  T* __restrict__ dz = reinterpret_cast<T*>(dz_);
+  const uint32_t CV = p.C / V, ga_cv = p.ga_c8 * (8 / V);
+  const uint32_t H = p.H, W = p.W, Hq = (H + 1) >> 1, Wq = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
   const uint32_t npix = (uint32_t)p.B * H * W, nquad = (uint32_t)p.B * Hq * Wq;
-  const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
+  const uint32_t cv = threadIdx.x % CV, lane_p = threadIdx.x / CV, ppb = blockDim.x / CV;
   const uint32_t stride = gridDim.x * ppb;
-  float sc[2][8], sh[2][8];
-  float ka[2][8], kb[2][8], kc[2][8];  // reduce: ka = mean, sums s1 / s2 in kb / kc;  apply: k0, kz, kc
+  float sc[2][V], sh[2][V];
+  float ka[2][V], kb[2][V], kc[2][V];  // reduce: ka = mean, sums s1 / s2 in kb / kc;  apply: k0, kz, kc
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    ld8f(p.scale + g * p.C + c8 * 8, sc[g]);
-    ld8f(p.shift + g * p.C + c8 * 8, sh[g]);
+    ldvf(p.scale + g * p.C + cv * V, sc[g]);
+    ldvf(p.shift + g * p.C + cv * V, sh[g]);
     if (APPLY) {
-      ld8f(coef + (g * 3 + 0) * p.C + c8 * 8, ka[g]);
-      ld8f(coef + (g * 3 + 1) * p.C + c8 * 8, kb[g]);
-      ld8f(coef + (g * 3 + 2) * p.C + c8 * 8, kc[g]);
+      ldvf(coef + (g * 3 + 0) * p.C + cv * V, ka[g]);
+      ldvf(coef + (g * 3 + 1) * p.C + cv * V, kb[g]);
+      ldvf(coef + (g * 3 + 2) * p.C + cv * V, kc[g]);
     } else {
-      ld8f(p.mean + g * p.C + c8 * 8, ka[g]);
+      ldvf(p.mean + g * p.C + cv * V, ka[g]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) kb[g][j] = kc[g][j] = 0.f;
+      for (int j = 0; j < V; ++j) kb[g][j] = kc[g][j] = 0.f;
     }
   }
   for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
     const uint32_t qx = q % Wq, t = q / Wq, qy = t % Hq, b = t / Hq;
-    uint4 zv[2][4], gq[4], gpv[2];
+    T zv[2][4], gq[4], gpv[2];
     bool ok[4];
     uint32_t pix[4];
 #pragma unroll
@@ -970,69 +1014,69 @@ __global__ void __launch_bounds__(128, 2) bn_bwd2q_kernel(BnBwd p, const float* 
       ok[d] = y < H && x < W;
       pix[d] = (b * H + y) * W + x;
       if (ok[d]) {
-        zv[0][d] = __ldg(p.z + (size_t)pix[d] * C8 + c8);
-        zv[1][d] = __ldg(p.z + (size_t)(npix + pix[d]) * C8 + c8);
-        gq[d] = __ldg(p.ga + (size_t)pix[d] * p.ga_c8 + c8);
+        zv[0][d] = __ldg(Z + (size_t)pix[d] * CV + cv);
+        zv[1][d] = __ldg(Z + (size_t)(npix + pix[d]) * CV + cv);
+        gq[d] = __ldg(GA + (size_t)pix[d] * ga_cv + cv);
       }
     }
     const bool pool_ok = GP && qy < Hp && qx < Wp;   // (then the whole window exists)
     if (pool_ok) {
-      gpv[0] = __ldg(p.gp + (size_t)((b * Hp + qy) * Wp + qx) * C8 + c8);
-      gpv[1] = __ldg(p.gp + (size_t)(((p.B + b) * Hp + qy) * Wp + qx) * C8 + c8);
+      gpv[0] = __ldg(GPP + (size_t)((b * Hp + qy) * Wp + qx) * CV + cv);
+      gpv[1] = __ldg(GPP + (size_t)(((p.B + b) * Hp + qy) * Wp + qx) * CV + cv);
     }
     // activations of both dates as the forward pass stored them (bf16), kept packed
-    uint4 av[2][4];
+    T av[2][4];
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int d = 0; d < 4; ++d)
         if (ok[d]) {
-          float af[8];
-          bn_act8<true>(zv[g][d], sc[g], sh[g], af);
-          av[g][d] = pack8(af);
+          float af[V];
+          bn_actv<V>(zv[g][d], sc[g], sh[g], af);
+          av[g][d] = packv(af);
         }
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       // arg-max of nn.MaxPool2d over the window: the FIRST maximum in scan order
-      int best[8];
-      float gpf[8];
+      int best[V];
+      float gpf[V];
       if (pool_ok) {
-        float m[8];
-        unpack8(av[g][0], m);
+        float m[V];
+        unpackv(av[g][0], m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] = 0;
+        for (int j = 0; j < V; ++j) best[j] = 0;
 #pragma unroll
         for (int d = 1; d < 4; ++d) {
-          float v[8];
-          unpack8(av[g][d], v);
+          float v[V];
+          unpackv(av[g][d], v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < V; ++j)
             if (v[j] > m[j]) m[j] = v[j], best[j] = d;
         }
-        unpack8(gpv[g], gpf);
+        unpackv(gpv[g], gpf);
       }
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         if (!ok[d]) continue;
-        float at[8], af[8], gaf[8], zf[8], dy[8];
-        unpack8(av[1 - g][d], at);
-        unpack8(av[g][d], af);
-        unpack8(gq[d], gaf);
-        unpack8(zv[g][d], zf);
+        float at[V], af[V], gaf[V], zf[V], dy[V];
+        unpackv(av[1 - g][d], at);
+        unpackv(av[g][d], af);
+        unpackv(gq[d], gaf);
+        unpackv(zv[g][d], zf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < V; ++j) {
           float v = gaf[j] * at[j];
           if (pool_ok && best[j] == d) v += gpf[j];
           dy[j] = af[j] > 0.f ? v : 0.f;
         }
         if (APPLY) {
-          float r[8];
+          float r[V];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaf(ka[g][j], dy[j], fmaf(kb[g][j], zf[j], kc[g][j]));
-          dz[(size_t)(g * npix + pix[d]) * C8 + c8] = pack8(r);
+          for (int j = 0; j < V; ++j) r[j] = fmaf(ka[g][j], dy[j], fmaf(kb[g][j], zf[j], kc[g][j]));
+          dz[(size_t)(g * npix + pix[d]) * CV + cv] = packv(r);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < V; ++j) {
             kb[g][j] += dy[j];
             kc[g][j] = fmaf(dy[j], zf[j] - ka[g][j], kc[g][j]);   // x invstd once, below
           }
@@ -1043,18 +1087,18 @@ __global__ void __launch_bounds__(128, 2) bn_bwd2q_kernel(BnBwd p, const float* 
   if (!APPLY) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      float is[8];
-      ld8f(p.invstd + g * p.C + c8 * 8, is);
+      float is[V];
+      ldvf(p.invstd + g * p.C + cv * V, is);
       __syncthreads();
-      float* mine = sm + threadIdx.x * 16;
+      float* mine = sm + threadIdx.x * (2 * V);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mine[j] = kb[g][j], mine[8 + j] = kc[g][j] * is[j];
+      for (int j = 0; j < V; ++j) mine[j] = kb[g][j], mine[V + j] = kc[g][j] * is[j];
       __syncthreads();
       float* dst = partial + ((size_t)blockIdx.x * p.G + g) * p.C * 2;
       for (int i = threadIdx.x; i < p.C * 2; i += blockDim.x) {
         const int c = i >> 1, k = i & 1;
         float s_ = 0.f;
-        for (uint32_t l = 0; l < ppb; ++l) s_ += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
+        for (uint32_t l = 0; l < ppb; ++l) s_ += sm[(l * CV + (c / V)) * (2 * V) + k * V + (c % V)];
         dst[i] = s_;
       }
     }
@@ -1167,6 +1211,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int S, int Cou
     float s = 0.f;
     for (int k = 0; k < S; ++k) s += ws[k * slab + o];
     dw[i] = s;
+  }
+}
+
+// The same for the operand-swapped launch (64-channel dL/dz against a >= 128-channel conv input: the INPUT's channels are the
+// M dimension, so all 128 MMA rows are useful instead of 64 x two filter rows = 75 %): ws holds
+//   dW'[ci][tap'][co] = sum_px X[px][ci] * dZ[px + tap'][co]  =  dW[co][8 - tap'][ci]        [S][Cin][9][Cout] fp32
+__global__ void wgrad_reduce_swapped_kernel(const float* __restrict__ ws, int S, int Cout, int Cin, float* __restrict__ dw) {
+  const size_t n = (size_t)Cout * Cin * 9;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // i walks ws' (coalesced reads); the 36-byte-strided writes of the small result are absorbed by L2
+    const int co = i % Cout, tp = (i / Cout) % 9, ci = i / ((size_t)9 * Cout);
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += ws[k * n + i];
+    dw[((size_t)co * Cin + ci) * 9 + (8 - tp)] = s;
   }
 }
 
@@ -1317,11 +1375,22 @@ int64_t fabric_b200_outconv_bwd_ws_floats(int C) {
   return (int64_t)(di.sms * 4 + 1) * (2 * C + 2);
 }
 
+// reduce-pass blocks per SM at most (the partial array is [blocks][G][C][2])
+constexpr int kBnBwdMaxBlk = 4;
+// channels per thread of the quad kernels: 4 (default) or 8 (FABRIC_B200_BWD2Q_V=8: the A/B switch)
+static int bwd2q_vec() {
+  static const int v = [] {
+    const char* e = getenv("FABRIC_B200_BWD2Q_V");
+    return (e && e[0] == '8') ? 8 : 4;
+  }();
+  return v;
+}
+
 int64_t fabric_b200_bn_bwd_ws_floats(int G, int C) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  return (int64_t)di.sms * 3 * G * C * 2 + (int64_t)G * 3 * C;
+  return (int64_t)di.sms * kBnBwdMaxBlk * G * C * 2 + (int64_t)G * 3 * C;
 }
 
 // phase bits: 1 = reduce pass (partials into ws), 2 = finalize + apply pass.  `count_scale` multiplies the per-group element
@@ -1350,18 +1419,23 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   p.G = G, p.B = B, p.H = H, p.W = W, p.C = C;
   p.premasked = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  // = resident blocks: one balanced wave (256 threads x 2 per SM; the recompute quad kernels 128 threads x 2 per SM)
-  const int nblk = di.sms * 2;
-  float* partial = ws;
-  float* coef = ws + (size_t)nblk * G * C * 2;
   // product-fused encoder levels: both date groups per thread (see bn_bwd2_dy)
   const bool dual = mul_other && G == 2 && ga && ga_groups == 1;
+  // quad kernels (activation recomputed): 4 channels per thread, 4 blocks of 128 threads per SM, where 128 % (C/4) == 0
+  const bool quad = dual && !a;
+  const int qv = (quad && bwd2q_vec() == 4 && C / 4 <= 128 && 128 % (C / 4) == 0) ? 4 : 8;
+  // = resident blocks: one balanced wave (256 threads x 2 per SM; the quad kernels 128 threads x 2 or 4 per SM)
+  const int nblk = di.sms * ((quad && qv == 4) ? 4 : 2);
+  float* partial = ws;
+  float* coef = ws + (size_t)nblk * G * C * 2;
   if (phase & 1) {
-    const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 16 * sizeof(float);
+    const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 2 * qv * sizeof(float);
     // (the recompute variants run nblk blocks of 128 threads: the partial layout [nblk][G][C][2] is the same)
-    if (dual && gp && !a) bn_bwd2q_kernel<true, false><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    if (quad && gp && qv == 4) bn_bwd2q_kernel<true, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    else if (quad && gp) bn_bwd2q_kernel<true, false, 8><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual && gp) bn_bwd2_reduce_kernel<true, false><<<nblk, 256, sm2, st>>>(p, partial);
-    else if (dual && !a) bn_bwd2q_kernel<false, false><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    else if (quad && qv == 4) bn_bwd2q_kernel<false, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    else if (quad) bn_bwd2q_kernel<false, false, 8><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual) bn_bwd2_reduce_kernel<false, false><<<nblk, 256, sm2, st>>>(p, partial);
     else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
     FB_CUDA(cudaGetLastError());
@@ -1373,11 +1447,13 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     const size_t n = (size_t)B * H * W * (C / 8);   // per date group; 256 threads is a multiple of C/8 for every supported C
     const int g2 = ew_grid(n, 256, di.sms);
     uint4* dzo = reinterpret_cast<uint4*>(dz);
-    const size_t nq = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);   // quad-threads per date
+    const size_t nq = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / qv);   // quad-threads per date
     const int g1 = ew_grid(nq, 128, di.sms);
-    if (dual && gp && !a) bn_bwd2q_kernel<true, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    if (quad && gp && qv == 4) bn_bwd2q_kernel<true, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    else if (quad && gp) bn_bwd2q_kernel<true, true, 8><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual && gp) bn_bwd2_apply_kernel<true, false><<<g2, 256, 0, st>>>(p, coef, dzo);
-    else if (dual && !a) bn_bwd2q_kernel<false, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    else if (quad && qv == 4) bn_bwd2q_kernel<false, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    else if (quad) bn_bwd2q_kernel<false, true, 8><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual) bn_bwd2_apply_kernel<false, false><<<g2, 256, 0, st>>>(p, coef, dzo);
     else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
     FB_CUDA(cudaGetLastError());
@@ -1433,7 +1509,7 @@ int64_t fabric_b200_bn_bwd_partial_floats(int G, int C) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  return (int64_t)di.sms * 3 * G * C * 2;
+  return (int64_t)di.sms * kBnBwdMaxBlk * G * C * 2;
 }
 
 int fabric_b200_bn_apply_relu_head(const void* z, const float* scale, const float* shift, void* a, const float* head_w,
@@ -1525,6 +1601,17 @@ int fabric_b200_wgrad_reduce(const float* ws, int splits, int Cout, int Cin, int
   if (!ws || !dw) return fail(FB_ERR_ARG, "null pointer");
   const size_t n = (size_t)Cout * Cin * 9;
   wgrad_reduce_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(ws, splits, Cout, Cin, CinPad, dw);
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+int fabric_b200_wgrad_reduce_swapped(const float* ws, int splits, int Cout, int Cin, float* dw, void* stream) {
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  if (!ws || !dw) return fail(FB_ERR_ARG, "null pointer");
+  const size_t n = (size_t)Cout * Cin * 9;
+  wgrad_reduce_swapped_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(ws, splits, Cout, Cin, dw);
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }

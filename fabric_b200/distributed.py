@@ -218,11 +218,19 @@ class DataParallelStep:
                 recs += struct.pack("<QQQQiiiiiiii", pptr + 4 * off, gptr + 4 * off, wf, wd, k, mode, off, cout, cin, cinpad, 0, 0)
                 off += k
                 n_chunks += 1
+        def emit_tiles(pptr, gptr, wf, wd, cout, cin, cinpad):
+            # mode 3: one record per (16 output channels x <= 128 input channels) tile of a 3x3 conv weight
+            nonlocal n_chunks, recs
+            for co0 in range(0, cout, 16):
+                for ci0 in range(0, cin, 128):
+                    recs += struct.pack("<QQQQiiiiiiii", pptr, gptr, wf, wd, min(16, cout - co0), 3, co0, cout, cin, cinpad,
+                                        ci0, min(128, cin - ci0))
+                    n_chunks += 1
         for p, v in zip(self.params, self.views[:np_]):
             pk = getattr(self, "_packed", {}).get(p) if self._managed else None
             if pk is not None:
                 cout, cin = p.shape[0], p.shape[1]
-                emit(p.data_ptr(), v.data_ptr(), p.numel(), 2, pk[0].data_ptr(), pk[1].data_ptr(), cout, cin, pk[0].shape[2])
+                emit_tiles(p.data_ptr(), v.data_ptr(), pk[0].data_ptr(), pk[1].data_ptr(), cout, cin, pk[0].shape[2])
             else:
                 emit(p.data_ptr(), v.data_ptr(), p.numel(), 0)
         n_sgd = n_chunks

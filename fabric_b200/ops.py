@@ -532,17 +532,31 @@ def up_input_bwd(dcat5: torch.Tensor, cs: int, h: int, w: int) -> torch.Tensor:
     return dlow
 
 
+# operand swap of the weight gradient for 64-channel dL/dz against a >= 128-channel input (up3.c1, up4.c1): the kernel's M
+# dimension (128 MMA rows) then carries the INPUT's channels instead of 64 dL/dz channels x two of the three filter rows
+# (75 % useful).  FABRIC_B200_WGRAD_SWAP=0 is the A/B switch.
+WGRAD_SWAP = os.environ.get("FABRIC_B200_WGRAD_SWAP", "1") != "0"
+
+
 def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: int = 0, wide=None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, swap=None) -> torch.Tensor:
     """dW [Cout,Cin,3,3] fp32 = autograd weight gradient of conv3x3(x5, W) given dL/dz (tcgen05, split-K).  ``out``: write
-    the gradient there (e.g. a view of the data-parallel gradient bucket)."""
+    the gradient there (e.g. a view of the data-parallel gradient bucket).  ``swap``: run the kernel with the operand roles
+    exchanged (see WGRAD_SWAP; None = automatic)."""
     lib = _lib.load()
     _need_cuda(dz5, x5, out)
     g, b, h, w, ca = dz5.shape
     cb = x5.shape[4]
+    if swap is None:
+        swap = WGRAD_SWAP and ca == 64 and cb >= 128 and cb % 128 == 0 and cin_true == cb
+    elif swap and not (cb % 64 == 0 and cin_true == cb):
+        raise ValueError("operand swap needs an unpadded input of a multiple of 64 channels")
     d = _lib.WgradDesc()
-    d.G, d.B, d.H, d.W, d.Ca, d.Cb = g, b, h, w, ca, cb
-    d.p, d.q = _p(dz5), _p(x5)
+    d.G, d.B, d.H, d.W = g, b, h, w
+    if swap:
+        d.Ca, d.Cb, d.p, d.q = cb, ca, _p(x5), _p(dz5)
+    else:
+        d.Ca, d.Cb, d.p, d.q = ca, cb, _p(dz5), _p(x5)
     d.splits = splits
     d.wide = WGRAD_WIDE if wide is None else int(wide)
     d.ws = 16  # planner only checks alignment/non-null later
@@ -560,7 +574,10 @@ def conv3x3_wgrad(dz5: torch.Tensor, x5: torch.Tensor, cin_true: int, splits: in
         prof.append((f"wgrad {cin_true}->{ca}@{h}x{w}xG{g}", e0, e1, 2.0 * g * b * h * w * 9 * cin_true * ca))
     dw = out if out is not None else _empty((ca, cin_true, 3, 3), dtype=torch.float32, device=dz5.device)
     assert dw.shape == (ca, cin_true, 3, 3) and dw.dtype == torch.float32
-    check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
+    if swap:
+        check(lib.fabric_b200_wgrad_reduce_swapped(_p(ws), s, ca, cin_true, _p(dw), _stream()), "wgrad_reduce")
+    else:
+        check(lib.fabric_b200_wgrad_reduce(_p(ws), s, ca, cin_true, cb, _p(dw), _stream()), "wgrad_reduce")
     _count(2)
     return dw
 

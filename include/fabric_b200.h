@@ -273,6 +273,10 @@ int fabric_b200_conv3x3_wgrad_splits(const fb_wgrad_desc* d);
 int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream);
 /* sum the split-K partials and transpose to nn.Conv2d layout: dw [Cout][Cin][3][3] fp32 */
 int fabric_b200_wgrad_reduce(const float* ws, int splits, int Cout, int Cin, int CinPad, float* dw, void* stream);
+/* the same after an operand-swapped fabric_b200_conv3x3_wgrad call (p = conv input, q = dL/dz, Ca = Cin, Cb = Cout: used
+   when dL/dz has 64 channels and the input >= 128, so that the input's channels fill the 128 MMA rows):
+   ws [splits][Cin][9][Cout] holds dW'[ci][tap'][co] = dW[co][8 - tap'][ci] */
+int fabric_b200_wgrad_reduce_swapped(const float* ws, int splits, int Cout, int Cin, float* dw, void* stream);
 
 /* ---- full-scene inference (reference utils/inference.py, utils/dataloaders.py:94-99, train.py:96-106) -- */
 

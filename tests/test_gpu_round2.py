@@ -620,7 +620,8 @@ def test_scene_row_bands_concatenate_to_the_single_rank_mask(cuda):
 
 
 def test_step_update_kernel_modes(cuda):
-    """fabric_b200_train_step_update: mode 0 (SGD), mode 1 (scale), mode 2 (SGD + packed refresh incl. the 13 -> 16 padded stem)"""
+    """fabric_b200_train_step_update: mode 0 (SGD), mode 1 (scale), mode 2 (SGD + packed refresh incl. the 13 -> 16 padded stem),
+    mode 3 (the same per 16 x 128-channel tile through shared memory: what DataParallelStep emits)"""
     import struct
     from fabric_b200 import _lib, ops
     torch.manual_seed(6)
@@ -644,12 +645,26 @@ def test_step_update_kernel_modes(cuda):
     emit(w.data_ptr(), gw.data_ptr(), w.numel(), 2, wf.data_ptr(), wd.data_ptr(), 64, 13, 16)
     emit(b.data_ptr(), gb.data_ptr(), b.numel(), 0)
     emit(st.data_ptr(), st.data_ptr(), st.numel(), 1)
+    # mode 3 on a weight with ragged tiles in both directions (40 = 16 + 16 + 8 output, 200 = 128 + 72 input channels)
+    w3 = torch.randn(40, 200, 3, 3, device=cuda)
+    g3 = torch.randn_like(w3)
+    w30 = w3.clone()
+    cp3 = ops.cpad(200)
+    wf3 = torch.zeros(40, 9, cp3, dtype=torch.bfloat16, device=cuda)
+    wd3 = torch.zeros(200, 9, 40, dtype=torch.bfloat16, device=cuda)
+    for co0 in range(0, 40, 16):
+        for ci0 in range(0, 200, 128):
+            recs += struct.pack("<QQQQiiiiiiii", w3.data_ptr(), g3.data_ptr(), wf3.data_ptr(), wd3.data_ptr(), min(16, 40 - co0), 3,
+                                co0, 40, 200, cp3, ci0, min(128, 200 - ci0))
+            n += 1
     table = torch.frombuffer(recs, dtype=torch.uint8).clone().to(cuda)
     _lib.check(_lib.load().fabric_b200_train_step_update(table.data_ptr(), n, 0.3, 0.5, 0.25, torch.cuda.current_stream().cuda_stream))
     lr = torch.tensor(0.3, dtype=torch.float32) * torch.tensor(0.5, dtype=torch.float32)
     assert torch.allclose(w, w0 - float(lr) * gw, rtol=0, atol=1e-6) and torch.allclose(b, b0 - float(lr) * gb, rtol=0, atol=1e-6)
     assert torch.equal(st, st0 * 0.25)
     assert torch.equal(wf, ops.pack_conv_weight(w, 0)) and torch.equal(wd, ops.pack_conv_weight(w, 1))
+    assert torch.allclose(w3, w30 - float(lr) * g3, rtol=0, atol=1e-6)
+    assert torch.equal(wf3, ops.pack_conv_weight(w3, 0)) and torch.equal(wd3, ops.pack_conv_weight(w3, 1))
 
 
 # ------------------------------------------------------------------------------------------------ CUDA graph step
