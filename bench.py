@@ -700,6 +700,18 @@ def main():
         rec = {"value": v, "unit": "patch-pairs/s", "h2d_bytes_per_step": res["b"][0], "d2h_bytes_per_step": res["b"][1],
                "steps": args.e2e_steps, "h2d_gbs_per_rank": res["b"][0] * args.e2e_steps / wall / 1e9,
                "api": f"fabric_b200.inference.HostPipeline.run (pinned fp32 NCHW in, fp32 logits out, {args.e2e_chunk}-pair sub-batches)"}
+        # what the host can deliver to this GPU when nothing else runs: the same pinned buffers copied in the same 32-pair
+        # sub-batches, no compute (with N ranks on one host all N copy at once: the aggregate is the platform's H2D ceiling)
+        dst = torch.empty(args.e2e_chunk, 13, SIZE, SIZE, device=dev)
+
+        def h2d_only():
+            for lo in range(0, PAIRS, args.e2e_chunk):
+                dst.copy_(hp1[lo:lo + args.e2e_chunk], non_blocking=True)
+                dst.copy_(hp2[lo:lo + args.e2e_chunk], non_blocking=True)
+        _, wall = timed_e2e(h2d_only, args.e2e_steps)
+        rec["h2d_only_gbs_per_rank"] = res["b"][0] * args.e2e_steps / wall / 1e9
+        rec["h2d_only_gbs_all_ranks"] = rec["h2d_only_gbs_per_rank"] * world      # (wall = max over ranks)
+        del dst
         if train:
             infer["e2e"] = rec
         else:
