@@ -63,6 +63,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int grid, in
 
 // a = relu(z * scale_g + shift_g) (+ 2x2 max pool) (+ relu(a_d2 * a_d1) into the decoder input).  One thread = 8 channels
 // of one 2x2 pixel quad, for BOTH date groups when the product is fused; 32-bit indexing.
+// EVEN: H and W even (every real level): no bounds tests, the quad is one basic block.
+template <bool EVEN>
 __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, uint4* __restrict__ a,
                                                           uint4* __restrict__ pool, uint4* __restrict__ prod, int prod_c8,
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restric
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-        ok[d] = y < (uint32_t)H && x < (uint32_t)W;
+        ok[d] = EVEN || (y < (uint32_t)H && x < (uint32_t)W);
         if (ok[d]) zin[d] = __ldg(z + (size_t)((img * H + y) * W + x) * C8 + c8);
       }
 #pragma unroll
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const uint4* __restric
           }
         }
       }
-      if (pool && qy < Hp && qx < Wp) pool[(size_t)((img * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
+      if (pool && (EVEN || (qy < Hp && qx < Wp))) pool[(size_t)((img * Hp + qy) * Wp + qx) * C8 + c8] = pack8(m);
     }
   }
 }
@@ -973,7 +975,27 @@ __device__ __forceinline__ void bn_actv(const T& zv, const float (&sc)[V], const
   unpackv(packv(zf), af);
 }
 
-template <bool GP, bool APPLY, int V>
+// EVEN: H and W are even (every real level), so every quad is whole and -- with GP -- has a pooled gradient: the per-pixel
+// bounds branches disappear, which is worth more than their own instructions: the quad becomes ONE basic block in which the
+// compiler shares the unpacked z / upstream-gradient values between the two dates and interleaves the four pixels.
+// ... and packed: max(x, 0) rides in the conversion (cvt.rn.relu.bf16x2: negative values and -0 become +0, exactly what
+// fmaxf(x, 0) followed by a round-to-nearest conversion stores)
+template <int V>
+__device__ __forceinline__ typename QVec<V>::type bn_act_packed(const typename QVec<V>::type& zv, const float (&sc)[V],
+                                                               const float (&sh)[V]) {
+  float zf[V];
+  unpackv(zv, zf);
+#pragma unroll
+  for (int j = 0; j < V; ++j) zf[j] = fmaf(zf[j], sc[j], sh[j]);
+  if constexpr (V == 8) {
+    return make_uint4(fb::pack_bf16x2_relu(zf[0], zf[1]), fb::pack_bf16x2_relu(zf[2], zf[3]), fb::pack_bf16x2_relu(zf[4], zf[5]),
+                      fb::pack_bf16x2_relu(zf[6], zf[7]));
+  } else {
+    return make_uint2(fb::pack_bf16x2_relu(zf[0], zf[1]), fb::pack_bf16x2_relu(zf[2], zf[3]));
+  }
+}
+
+template <bool GP, bool APPLY, int V, bool EVEN = false>
 __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz_,
                                                                      float* __restrict__ partial) {
   using T = typename QVec<V>::type;
@@ -1011,7 +1033,7 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
-      ok[d] = y < H && x < W;
+      ok[d] = EVEN || (y < H && x < W);
       pix[d] = (b * H + y) * W + x;
       if (ok[d]) {
         zv[0][d] = __ldg(Z + (size_t)pix[d] * CV + cv);
@@ -1019,7 +1041,7 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
         gq[d] = __ldg(GA + (size_t)pix[d] * ga_cv + cv);
       }
     }
-    const bool pool_ok = GP && qy < Hp && qx < Wp;   // (then the whole window exists)
+    const bool pool_ok = GP && (EVEN || (qy < Hp && qx < Wp));   // (then the whole window exists)
     if (pool_ok) {
       gpv[0] = __ldg(GPP + (size_t)((b * Hp + qy) * Wp + qx) * CV + cv);
       gpv[1] = __ldg(GPP + (size_t)(((p.B + b) * Hp + qy) * Wp + qx) * CV + cv);
@@ -1030,45 +1052,42 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int d = 0; d < 4; ++d)
-        if (ok[d]) {
-          float af[V];
-          bn_actv<V>(zv[g][d], sc[g], sh[g], af);
-          av[g][d] = packv(af);
-        }
+        if (ok[d]) av[g][d] = bn_act_packed<V>(zv[g][d], sc[g], sh[g]);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      // arg-max of nn.MaxPool2d over the window: the FIRST maximum in scan order
-      int best[V];
-      float gpf[V];
+      float A[4][V], v[4][V];   // own activation; upstream gradient through the product = ga * (other date's activation)
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        if (!ok[d]) continue;
+        float at[V], gaf[V];
+        unpackv(av[g][d], A[d]);
+        unpackv(av[1 - g][d], at);
+        unpackv(gq[d], gaf);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[d][j] = gaf[j] * at[j];
+      }
       if (pool_ok) {
-        float m[V];
-        unpackv(av[g][0], m);
-#pragma unroll
-        for (int j = 0; j < V; ++j) best[j] = 0;
-#pragma unroll
-        for (int d = 1; d < 4; ++d) {
-          float v[V];
-          unpackv(av[g][d], v);
-#pragma unroll
-          for (int j = 0; j < V; ++j)
-            if (v[j] > m[j]) m[j] = v[j], best[j] = d;
-        }
+        // nn.MaxPool2d backward: the pooled gradient goes to the FIRST maximum of the window in scan order
+        float gpf[V];
         unpackv(gpv[g], gpf);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float m = fmaxf(fmaxf(A[0][j], A[1][j]), fmaxf(A[2][j], A[3][j]));
+          const bool e0 = A[0][j] == m, e1 = A[1][j] == m, e2 = A[2][j] == m;   // (bitwise: no short-circuit branches)
+          const bool p0 = e0, p1 = !e0 & e1, p2 = !e0 & !e1 & e2;
+          v[0][j] += p0 ? gpf[j] : 0.f;           // (selects, not branches: the four lanes of a warp disagree)
+          v[1][j] += p1 ? gpf[j] : 0.f;
+          v[2][j] += p2 ? gpf[j] : 0.f;
+          v[3][j] += (e0 | e1 | e2) ? 0.f : gpf[j];
+        }
       }
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         if (!ok[d]) continue;
-        float at[V], af[V], gaf[V], zf[V], dy[V];
-        unpackv(av[1 - g][d], at);
-        unpackv(av[g][d], af);
-        unpackv(gq[d], gaf);
+        float zf[V], dy[V];
         unpackv(zv[g][d], zf);
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          float v = gaf[j] * at[j];
-          if (pool_ok && best[j] == d) v += gpf[j];
-          dy[j] = af[j] > 0.f ? v : 0.f;
-        }
+        for (int j = 0; j < V; ++j) dy[j] = A[d][j] > 0.f ? v[d][j] : 0.f;
         if (APPLY) {
           float r[V];
 #pragma unroll
@@ -1261,7 +1280,8 @@ int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* sh
   if ((double)G * B * H * W * C / 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   if (prod_out && (G != 2 || prod_channels < C || prod_channels % 8)) return fail(FB_ERR_SHAPE, "product fusion needs G == 2 and prod_channels >= C");
   const size_t n = (size_t)(prod_out ? 1 : G) * B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  bn_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+  auto kern = (H % 2 == 0 && W % 2 == 0) ? bn_apply_kernel<true> : bn_apply_kernel<false>;
+  kern<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<uint4*>(a), reinterpret_cast<uint4*>(pool_out),
       reinterpret_cast<uint4*>(prod_out), prod_channels / 8, G, B, H, W, C);
   FB_CUDA(cudaGetLastError());
@@ -1381,7 +1401,7 @@ constexpr int kBnBwdMaxBlk = 4;
 static int bwd2q_vec() {
   static const int v = [] {
     const char* e = getenv("FABRIC_B200_BWD2Q_V");
-    return (e && e[0] == '8') ? 8 : 4;
+    return (e && e[0] == '8') ? 8 : (e && e[0] == '5') ? 5 : 4;
   }();
   return v;
 }
@@ -1423,7 +1443,8 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   const bool dual = mul_other && G == 2 && ga && ga_groups == 1;
   // quad kernels (activation recomputed): 4 channels per thread, 4 blocks of 128 threads per SM, where 128 % (C/4) == 0
   const bool quad = dual && !a;
-  const int qv = (quad && bwd2q_vec() == 4 && C / 4 <= 128 && 128 % (C / 4) == 0) ? 4 : 8;
+  const int qv = (quad && bwd2q_vec() != 8 && C / 4 <= 128 && 128 % (C / 4) == 0) ? 4 : 8;
+  const bool even = H % 2 == 0 && W % 2 == 0 && bwd2q_vec() != 5;   // (FABRIC_B200_BWD2Q_V=5: 4 channels, generic quads)
   // = resident blocks: one balanced wave (256 threads x 2 per SM; the quad kernels 128 threads x 2 or 4 per SM)
   const int nblk = di.sms * ((quad && qv == 4) ? 4 : 2);
   float* partial = ws;
@@ -1431,7 +1452,8 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   if (phase & 1) {
     const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 2 * qv * sizeof(float);
     // (the recompute variants run nblk blocks of 128 threads: the partial layout [nblk][G][C][2] is the same)
-    if (quad && gp && qv == 4) bn_bwd2q_kernel<true, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, false, 4, true><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    else if (quad && gp && qv == 4) bn_bwd2q_kernel<true, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (quad && gp) bn_bwd2q_kernel<true, false, 8><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual && gp) bn_bwd2_reduce_kernel<true, false><<<nblk, 256, sm2, st>>>(p, partial);
     else if (quad && qv == 4) bn_bwd2q_kernel<false, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
@@ -1449,7 +1471,8 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     uint4* dzo = reinterpret_cast<uint4*>(dz);
     const size_t nq = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / qv);   // quad-threads per date
     const int g1 = ew_grid(nq, 128, di.sms);
-    if (quad && gp && qv == 4) bn_bwd2q_kernel<true, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, true, 4, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    else if (quad && gp && qv == 4) bn_bwd2q_kernel<true, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (quad && gp) bn_bwd2q_kernel<true, true, 8><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual && gp) bn_bwd2_apply_kernel<true, false><<<g2, 256, 0, st>>>(p, coef, dzo);
     else if (quad && qv == 4) bn_bwd2q_kernel<false, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
