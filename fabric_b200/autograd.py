@@ -82,7 +82,8 @@ def _dc_forward(dc, x5, pool, prod_out=None, head=None):
     # recomputes it from z2 (bit-identically) -- it never touches HBM.  (KEEP_SAVED: tests want to look at it.)
     skip_a = RECOMPUTE_ENCODER_ACT and pool and prod_out is not None and not KEEP_SAVED
     if head is not None:
-        a2, pooled = ops.bn_apply_relu_head(r2["y"], s2[0], s2[1], head.conv.weight, head.conv.bias)
+        # (the head's backward recomputes the activation from z2: it is stored only for tests that look at it)
+        a2, pooled = ops.bn_apply_relu_head(r2["y"], s2[0], s2[1], head.conv.weight, head.conv.bias, write_a=KEEP_SAVED)
     else:
         a2, pooled = ops.bn_apply_relu(r2["y"], s2[0], s2[1], pool=pool, prod_out=prod_out, write_a=not skip_a)
     saved = dict(x=x5, z1=r1["y"], a1=a1, z2=r2["y"], a2=a2, s1=s1, s2=s2)

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) bn_apply_head_kernel(const uint4* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
       const uint4 av = pack8(f);
-      if (live) a[(size_t)pix * 8 + c8] = av;
+      if (live && a) a[(size_t)pix * 8 + c8] = av;
       unpack8(av, q);   // the head sees the activation as stored
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
@@ -195,7 +195,11 @@ struct HeadBwd {
   const float* invstd;
   const float* hw;
   uint32_t npix, plane;
+  unsigned long long plane_magic;   // ceil(2^40 / plane) when npix * plane < 2^40 (pix / plane as one multiply), else 0
 };
+__device__ __forceinline__ uint32_t head_image(const HeadBwd& p, uint32_t pix) {
+  return p.plane_magic ? (uint32_t)(((unsigned long long)pix * p.plane_magic) >> 40) : pix / p.plane;
+}
 constexpr int kHeadPartial = 64 * 2 + 2 * 64 + 2;
 
 __global__ void __launch_bounds__(256, 2) bn_head_bwd_reduce_kernel(HeadBwd p, float* __restrict__ partial) {
@@ -213,44 +217,45 @@ __global__ void __launch_bounds__(256, 2) bn_head_bwd_reduce_kernel(HeadBwd p, f
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = g0[j] = g1[j] = 0.f;
   const uint32_t stride = gridDim.x * ppb;
   constexpr int NB = 4;
-  for (uint32_t p0 = blockIdx.x * ppb + lane_p; p0 < p.npix; p0 += NB * stride) {
+  auto load = [&](uint32_t pix, uint4& zr, float& dl0, float& dl1) {
+    const uint32_t b = head_image(p, pix), o = pix - b * p.plane;
+    zr = __ldg(p.z + (size_t)pix * 8 + c8);
+    dl0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
+    dl1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+  };
+  auto one = [&](const uint4& zr, float d0, float d1) {
+    float zf[8], pre[8];
+    unpack8(zr, zf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pre[j] = fmaf(zf[j], sc[j], sh[j]);
+    float aq[8];
+    // as stored by the forward pass: max(x, 0) rides in the bf16 conversion
+    unpack8(make_uint4(fb::pack_bf16x2_relu(pre[0], pre[1]), fb::pack_bf16x2_relu(pre[2], pre[3]), fb::pack_bf16x2_relu(pre[4], pre[5]),
+                       fb::pack_bf16x2_relu(pre[6], pre[7])), aq);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dy = pre[j] > 0.f ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
+      s1[j] += dy;
+      s2[j] = fmaf(dy, (zf[j] - mu[j]) * is[j], s2[j]);
+      g0[j] = fmaf(d0, aq[j], g0[j]);
+      g1[j] = fmaf(d1, aq[j], g1[j]);
+    }
+    if (c8 == 0) d0s += d0, d1s += d1;
+  };
+  uint32_t p0 = blockIdx.x * ppb + lane_p;
+  for (; p0 + (NB - 1) * stride < p.npix; p0 += NB * stride) {   // main loop: four pixels in flight, no bounds tests
     uint4 zr[NB];
     float dl0[NB], dl1[NB];
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const uint32_t pix = p0 + k * stride;
-      if (pix < p.npix) {
-        const uint32_t b = pix / p.plane, o = pix - b * p.plane;
-        zr[k] = __ldg(p.z + (size_t)pix * 8 + c8);
-        dl0[k] = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
-        dl1[k] = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
-      }
-    }
+    for (int k = 0; k < NB; ++k) load(p0 + k * stride, zr[k], dl0[k], dl1[k]);
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      if (p0 + k * stride >= p.npix) break;
-      const float d0 = dl0[k], d1 = dl1[k];
-      float zf[8], af[8];
-      unpack8(zr[k], zf);
-      bool on[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float pre = fmaf(zf[j], sc[j], sh[j]);
-        on[j] = pre > 0.f;
-        af[j] = fmaxf(pre, 0.f);
-      }
-      float aq[8];
-      unpack8(pack8(af), aq);   // as stored by the forward pass
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dy = on[j] ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
-        s1[j] += dy;
-        s2[j] = fmaf(dy, (zf[j] - mu[j]) * is[j], s2[j]);
-        g0[j] = fmaf(d0, aq[j], g0[j]);
-        g1[j] = fmaf(d1, aq[j], g1[j]);
-      }
-      if (c8 == 0) d0s += d0, d1s += d1;
-    }
+    for (int k = 0; k < NB; ++k) one(zr[k], dl0[k], dl1[k]);
+  }
+  for (; p0 < p.npix; p0 += stride) {
+    uint4 zr;
+    float d0, d1;
+    load(p0, zr, d0, d1);
+    one(zr, d0, d1);
   }
   float* mine = sm + threadIdx.x * 34;
 #pragma unroll
@@ -311,32 +316,36 @@ __global__ void __launch_bounds__(256, 2) bn_head_bwd_apply_kernel(HeadBwd p, co
   ld8f(coef + 128 + c8 * 8, kc);
   const uint32_t pstride = (gridDim.x * blockDim.x) >> 3;
   constexpr int NB = 4;
-  for (uint32_t p0 = gtid >> 3; p0 < p.npix; p0 += NB * pstride) {
+  auto load = [&](uint32_t pix, uint4& zr, float& dl0, float& dl1) {
+    const uint32_t b = head_image(p, pix), o = pix - b * p.plane;
+    zr = __ldg(p.z + (size_t)pix * 8 + c8);
+    dl0 = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
+    dl1 = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
+  };
+  auto one = [&](uint32_t pix, const uint4& zr, float d0, float d1) {
+    float zf[8], r[8];
+    unpack8(zr, zf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dy = fmaf(zf[j], sc[j], sh[j]) > 0.f ? fmaf(d0, w0[j], d1 * w1[j]) : 0.f;
+      r[j] = fmaf(k0[j], dy, fmaf(kz[j], zf[j], kc[j]));
+    }
+    dz[(size_t)pix * 8 + c8] = pack8(r);
+  };
+  uint32_t p0 = gtid >> 3;
+  for (; p0 + (NB - 1) * pstride < p.npix; p0 += NB * pstride) {
     uint4 zr[NB];
     float dl0[NB], dl1[NB];
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const uint32_t pix = p0 + k * pstride;
-      if (pix < p.npix) {
-        const uint32_t b = pix / p.plane, o = pix - b * p.plane;
-        zr[k] = __ldg(p.z + (size_t)pix * 8 + c8);
-        dl0[k] = __ldg(p.dlogits + (size_t)(b * 2) * p.plane + o);
-        dl1[k] = __ldg(p.dlogits + (size_t)(b * 2 + 1) * p.plane + o);
-      }
-    }
+    for (int k = 0; k < NB; ++k) load(p0 + k * pstride, zr[k], dl0[k], dl1[k]);
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const uint32_t pix = p0 + k * pstride;
-      if (pix >= p.npix) break;
-      float zf[8], r[8];
-      unpack8(zr[k], zf);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dy = fmaf(zf[j], sc[j], sh[j]) > 0.f ? fmaf(dl0[k], w0[j], dl1[k] * w1[j]) : 0.f;
-        r[j] = fmaf(k0[j], dy, fmaf(kz[j], zf[j], kc[j]));
-      }
-      dz[(size_t)pix * 8 + c8] = pack8(r);
-    }
+    for (int k = 0; k < NB; ++k) one(p0 + k * pstride, zr[k], dl0[k], dl1[k]);
+  }
+  for (; p0 < p.npix; p0 += pstride) {
+    uint4 zr;
+    float d0, d1;
+    load(p0, zr, d0, d1);
+    one(p0, zr, d0, d1);
   }
 }
 
@@ -759,6 +768,118 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwd p, const flo
         for (int j = 0; j < 8; ++j) r[j] = fmaf(k0[j], dy[j], fmaf(kz[j], zf[j], kc[j]));
         dz[(size_t)(g * npix + pix) * C8 + c8] = pack8(r);
       }
+    }
+  }
+}
+
+// The same two passes for the PLAIN case (decoder levels and every first conv: one gradient source, no product, no pool):
+// compile-time shape of the loop instead of the run-time flags of BnBwd -- four pixels in flight, no per-pixel bounds
+// tests in the main loop, one basic block per iteration.  MASK: apply the ReLU mask from z (false = the producing data-gradient
+// launch already masked dy).  (The generic kernels above measured 4.4-5.4 TB/s on these layers.)
+template <bool MASK>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_plain_kernel(const uint4* __restrict__ z, const uint4* __restrict__ ga,
+                                                                    uint32_t ga_c8, int ga_groups, const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift, const float* __restrict__ coef,
+                                                                    uint4* __restrict__ dz, int G, uint32_t npix, int C) {
+  constexpr int NB = 4;
+  const uint32_t C8 = C >> 3;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8 = gtid % C8;
+  const uint32_t pstride = (gridDim.x * blockDim.x) / C8;   // host guarantees divisibility
+  for (uint32_t g = 0; g < (uint32_t)G; ++g) {
+    float sc[8], sh[8], k0[8], kz[8], kc[8];
+    if (MASK) {
+      ld8f(scale + g * C + c8 * 8, sc);
+      ld8f(shift + g * C + c8 * 8, sh);
+    }
+    ld8f(coef + (g * 3 + 0) * C + c8 * 8, k0);
+    ld8f(coef + (g * 3 + 1) * C + c8 * 8, kz);
+    ld8f(coef + (g * 3 + 2) * C + c8 * 8, kc);
+    const uint4* zg = z + (size_t)g * npix * C8 + c8;
+    const uint4* gg = ga + (ga_groups == 1 ? (size_t)0 : (size_t)g * npix * ga_c8) + c8;
+    uint4* og = dz + (size_t)g * npix * C8 + c8;
+    auto one = [&](const uint4& zv, const uint4& gv, uint32_t pix) {
+      float zf[8], dy[8], r[8];
+      unpack8(zv, zf);
+      unpack8(gv, dy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MASK && !(fmaf(zf[j], sc[j], sh[j]) > 0.f)) dy[j] = 0.f;
+        r[j] = fmaf(k0[j], dy[j], fmaf(kz[j], zf[j], kc[j]));
+      }
+      og[(size_t)pix * C8] = pack8(r);
+    };
+    uint32_t q = gtid / C8;
+    for (; q + (NB - 1) * pstride < npix; q += NB * pstride) {
+      uint4 zv[NB], gv[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        zv[k] = __ldg(zg + (size_t)(q + k * pstride) * C8);
+        gv[k] = __ldg(gg + (size_t)(q + k * pstride) * ga_c8);
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) one(zv[k], gv[k], q + k * pstride);
+    }
+    for (; q < npix; q += pstride) one(__ldg(zg + (size_t)q * C8), __ldg(gg + (size_t)q * ga_c8), q);
+  }
+}
+
+// pass 1 of the plain case: partial[blk][g][c][2] = (sum dy, sum dy * xhat), dy = relu'(z) * ga
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_plain_kernel(const uint4* __restrict__ z, const uint4* __restrict__ ga,
+                                                                     uint32_t ga_c8, int ga_groups, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd, float* __restrict__ partial,
+                                                                     int G, uint32_t npix, int C) {
+  extern __shared__ float sm[];  // [blockDim][16]
+  constexpr int NB = 4;
+  const uint32_t C8 = C >> 3;
+  const uint32_t c8 = threadIdx.x % C8, lane_p = threadIdx.x / C8, ppb = blockDim.x / C8;
+  const uint32_t pstride = gridDim.x * ppb;
+  for (uint32_t g = 0; g < (uint32_t)G; ++g) {
+    float s1[8], s2[8], mu[8], sc[8], sh[8];
+    ld8f(mean + g * C + c8 * 8, mu);
+    ld8f(scale + g * C + c8 * 8, sc);
+    ld8f(shift + g * C + c8 * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const uint4* zg = z + (size_t)g * npix * C8 + c8;
+    const uint4* gg = ga + (ga_groups == 1 ? (size_t)0 : (size_t)g * npix * ga_c8) + c8;
+    auto one = [&](const uint4& zv, const uint4& gv) {
+      float zf[8], dy[8];
+      unpack8(zv, zf);
+      unpack8(gv, dy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!(fmaf(zf[j], sc[j], sh[j]) > 0.f)) dy[j] = 0.f;
+        s1[j] += dy[j];
+        s2[j] = fmaf(dy[j], zf[j] - mu[j], s2[j]);   // x invstd once, below
+      }
+    };
+    uint32_t q = blockIdx.x * ppb + lane_p;
+    for (; q + (NB - 1) * pstride < npix; q += NB * pstride) {
+      uint4 zv[NB], gv[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        zv[k] = __ldg(zg + (size_t)(q + k * pstride) * C8);
+        gv[k] = __ldg(gg + (size_t)(q + k * pstride) * ga_c8);
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) one(zv[k], gv[k]);
+    }
+    for (; q < npix; q += pstride) one(__ldg(zg + (size_t)q * C8), __ldg(gg + (size_t)q * ga_c8));
+    float is[8];
+    ld8f(invstd + g * C + c8 * 8, is);
+    __syncthreads();
+    float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[j] = s1[j], mine[8 + j] = s2[j] * is[j];
+    __syncthreads();
+    float* dst = partial + ((size_t)blockIdx.x * G + g) * C * 2;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+      const int c = i >> 1, k = i & 1;
+      float s = 0.f;
+      for (uint32_t l = 0; l < ppb; ++l) s += sm[(l * C8 + (c >> 3)) * 16 + k * 8 + (c & 7)];
+      dst[i] = s;
     }
   }
 }
@@ -1446,7 +1567,10 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   const int qv = (quad && bwd2q_vec() != 8 && C / 4 <= 128 && 128 % (C / 4) == 0) ? 4 : 8;
   const bool even = H % 2 == 0 && W % 2 == 0 && bwd2q_vec() != 5;   // (FABRIC_B200_BWD2Q_V=5: 4 channels, generic quads)
   // = resident blocks: one balanced wave (256 threads x 2 per SM; the quad kernels 128 threads x 2 or 4 per SM)
-  const int nblk = di.sms * ((quad && qv == 4) ? 4 : 2);
+  // plain case (one gradient source, no product / pool): the specialised kernels, 3 blocks of 256 threads per SM
+  const bool plain = ga && !gp && !mul_other && bwd2q_vec() != 8;
+  const uint32_t npix_ = (uint32_t)B * H * W;
+  const int nblk = di.sms * ((quad && qv == 4) ? 4 : plain ? 3 : 2);
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
   if (phase & 1) {
@@ -1459,6 +1583,7 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     else if (quad && qv == 4) bn_bwd2q_kernel<false, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (quad) bn_bwd2q_kernel<false, false, 8><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual) bn_bwd2_reduce_kernel<false, false><<<nblk, 256, sm2, st>>>(p, partial);
+    else if (plain) bn_bwd_reduce_plain_kernel<<<nblk, 256, sm2, st>>>(p.z, p.ga, p.ga_c8, ga_groups, scale, shift, mean, invstd, partial, G, npix_, C);
     else bn_bwd_reduce_kernel<<<nblk, 256, 256 * 16 * sizeof(float), st>>>(p, partial);
     FB_CUDA(cudaGetLastError());
   }
@@ -1478,6 +1603,7 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     else if (quad && qv == 4) bn_bwd2q_kernel<false, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (quad) bn_bwd2q_kernel<false, true, 8><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual) bn_bwd2_apply_kernel<false, false><<<g2, 256, 0, st>>>(p, coef, dzo);
+    else if (plain) bn_bwd_apply_plain_kernel<true><<<g2, 256, 0, st>>>(p.z, p.ga, p.ga_c8, ga_groups, scale, shift, coef, dzo, G, npix_, C);
     else bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef, reinterpret_cast<uint4*>(dz));
     FB_CUDA(cudaGetLastError());
   }
@@ -1523,7 +1649,11 @@ int fabric_b200_bn_bwd_from_partials(const void* z, const void* dy, const float*
                                                       mean, dgamma, dbeta, coef_ws, grad_scale, n_tile);
   FB_CUDA(cudaGetLastError());
   const size_t n = (size_t)B * H * W * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef_ws, reinterpret_cast<uint4*>(dz));
+  if (bwd2q_vec() != 8)
+    bn_bwd_apply_plain_kernel<false><<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p.z, p.ga, p.ga_c8, G, mean, mean, coef_ws,
+                                                                              reinterpret_cast<uint4*>(dz), G, (uint32_t)B * H * W, C);
+  else
+    bn_bwd_apply_kernel<<<ew_grid(n, 256, di.sms), 256, 0, st>>>(p, coef_ws, reinterpret_cast<uint4*>(dz));
   FB_CUDA(cudaGetLastError());
   return FB_OK;
 }
@@ -1540,7 +1670,7 @@ int fabric_b200_bn_apply_relu_head(const void* z, const float* scale, const floa
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  if (!z || !scale || !shift || !a || !head_w || !head_b || !logits) return fail(FB_ERR_ARG, "null pointer");
+  if (!z || !scale || !shift || !head_w || !head_b || !logits) return fail(FB_ERR_ARG, "null pointer");   // (a may be NULL)
   if (C != 64) return fail(FB_ERR_SHAPE, "the fused head is built for 64 channels (outc = outconv(64, 2), bidate_model.py:20)");
   if ((double)B * H * W * 8 >= 4.0e9) return fail(FB_ERR_SHAPE, "tensor too large for 32-bit indexing");
   const uint32_t npix = (uint32_t)B * H * W;
@@ -1572,6 +1702,7 @@ int fabric_b200_bn_head_bwd(int phase, const float* dlogits, const void* z, cons
   HeadBwd p;
   p.z = reinterpret_cast<const uint4*>(z), p.dlogits = dlogits, p.scale = scale, p.shift = shift, p.mean = mean, p.invstd = invstd;
   p.hw = head_w, p.npix = (uint32_t)B * H * W, p.plane = (uint32_t)H * W;
+  p.plane_magic = ((unsigned long long)p.npix * p.plane < (1ull << 40)) ? ((1ull << 40) + p.plane - 1) / p.plane : 0ull;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = di.sms * 2;
   float* partial = ws;

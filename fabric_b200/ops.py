@@ -379,12 +379,15 @@ def bn_apply_relu(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, po
     return a, pl
 
 
-def bn_apply_relu_head(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, head_w: torch.Tensor, head_b: torch.Tensor):
-    """up4's last BatchNorm + ReLU and `outconv` in one pass: returns (a [1,B,H,W,64] bf16, logits [B,2,H,W] fp32)."""
+def bn_apply_relu_head(z5: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, head_w: torch.Tensor, head_b: torch.Tensor,
+                       write_a: bool = True):
+    """up4's last BatchNorm + ReLU and `outconv` in one pass: returns (a [1,B,H,W,64] bf16, logits [B,2,H,W] fp32).
+    ``write_a=False``: the activation is not stored (returns None for it) -- the training step's backward recomputes it from
+    z (``bn_head_bwd``), so the 0.54 GB tensor need not touch HBM."""
     _need_cuda(z5, scale, shift, head_w, head_b)
     g, b, h, w, c = z5.shape
     assert g == 1 and head_w.shape[0] == 2
-    a = _empty_like(z5)
+    a = _empty_like(z5) if write_a else None
     logits = _empty((b, 2, h, w), dtype=torch.float32, device=z5.device)
     check(_lib.load().fabric_b200_bn_apply_relu_head(_p(z5), _p(scale), _p(shift), _p(a),
                                                      _p(head_w.detach().reshape(2, c).contiguous()), _p(head_b.detach()),

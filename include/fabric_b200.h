@@ -169,7 +169,8 @@ int fabric_b200_bn_apply_relu(const void* z, const float* scale, const float* sh
                               int prod_channels, int G, int B, int H, int W, int C, void* stream);
 
 /* The last decoder BatchNorm + ReLU (up4, 64 channels) and `outconv` (unet_parts.py:83-90, bidate_model.py:38-39) in ONE
- * pass: a = relu(z*scale+shift) stored as bf16 [B][H][W][64] and logits = W a + b as fp32 NCHW [B][2][H][W]. */
+ * pass: a = relu(z*scale+shift) stored as bf16 [B][H][W][64] (a may be NULL: not stored -- the backward entry point below
+ * recomputes it from z) and logits = W a + b as fp32 NCHW [B][2][H][W]. */
 int fabric_b200_bn_apply_relu_head(const void* z, const float* scale, const float* shift, void* a, const float* head_w,
                                    const float* head_b, float* logits, int B, int H, int W, int C, void* stream);
 /* ... and their backward, also fused: du = W^T dlogits is never materialised (dy = relu'(.) * du is recomputed from

@@ -1,10 +1,10 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
 echo "== pytest -m gpu"
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/r02r_pytest_gpu.log 2>&1; grep -E "^(FAILED|ERROR)|^E  +" $O/r02r_pytest_gpu.log | cut -c1-400 | head -20; tail -2 $O/r02r_pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/r02s_pytest_gpu.log 2>&1; grep -E "^(FAILED|ERROR)|^E  +" $O/r02s_pytest_gpu.log | cut -c1-400 | head -20; tail -2 $O/r02s_pytest_gpu.log
 F="--steps 1 --warmup 3 --no-cpu-baseline --no-library --no-scene --no-infer --no-small --e2e-steps 1"
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum --clock-control none -k regex:"bn_bwd2q|bn_apply_kernel" --csv --log-file $O/r02r_bn.csv python bench.py $F > /dev/null 2>&1
-python - $O/r02r_bn.csv <<'PY'
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum --clock-control none -k regex:"bn_bwd_apply|bn_bwd_reduce|bn_head|bn_apply_head" --csv --log-file $O/r02s_bn.csv python bench.py $F > /dev/null 2>&1
+python - $O/r02s_bn.csv <<'PY'
 import csv,sys
 from collections import defaultdict
 rows=list(csv.reader(open(sys.argv[1])))
@@ -14,7 +14,7 @@ for r in rows[i+1:]:
     if len(r)<len(h): continue
     rec=dict(zip(h,r)); d[rec['ID']]['k']=rec['Kernel Name'][:48]; d[rec['ID']][rec['Metric Name']]=rec['Metric Value']
 ids=sorted(d,key=int)
-n=len(ids)//4   # 4 steps captured (3 warm + 1): print the last
+n=len(ids)//4
 tot=defaultdict(float)
 for k in ids[-n:]:
     r=d[k]; t=float(r['gpu__time_duration.sum'])/1e3; b=(float(r['dram__bytes_read.sum'])+float(r['dram__bytes_write.sum']))/1e9
