@@ -1342,15 +1342,29 @@ __global__ void __launch_bounds__(256) up_input_bwd_rows_kernel(const uint4* __r
 }
 
 // fp32 [S][Cout][9][CinPad] split-K partials -> nn.Conv2d weight gradient [Cout][Cin][3][3]
+// One thread = four consecutive input channels of one (co, tap): the S partial slabs are read as float4 in their own order
+// (coalesced; the first version walked the RESULT order and read 4 bytes per 128-byte line), the 36-byte-strided writes of the
+// small result are absorbed by L2.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int S, int Cout, int Cin, int CinPad, float* __restrict__ dw) {
-  const size_t n = (size_t)Cout * Cin * 9;
   const size_t slab = (size_t)Cout * 9 * CinPad;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int tap = i % 9, ci = (i / 9) % Cin, co = i / ((size_t)9 * Cin);
-    const size_t o = ((size_t)co * 9 + tap) * CinPad + ci;
-    float s = 0.f;
-    for (int k = 0; k < S; ++k) s += ws[k * slab + o];
-    dw[i] = s;
+  const size_t n4 = slab >> 2;   // CinPad is a multiple of 16
+  const int cp4 = CinPad >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cp4) * 4;
+    if (ci >= Cin) continue;      // channel padding (13 -> 16)
+    const size_t row = i / cp4;   // co * 9 + tap
+    const int tap = (int)(row % 9);
+    const size_t co = row / 9;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < S; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + k * slab) + i);
+      s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    float* dst = dw + (co * Cin + ci) * 9 + tap;
+    dst[0] = s.x;
+    if (ci + 1 < Cin) dst[9] = s.y;
+    if (ci + 2 < Cin) dst[18] = s.z;
+    if (ci + 3 < Cin) dst[27] = s.w;
   }
 }
 
@@ -1753,7 +1767,8 @@ int fabric_b200_wgrad_reduce(const float* ws, int splits, int Cout, int Cin, int
   int rc = device_info(&di);
   if (rc) return rc;
   if (!ws || !dw) return fail(FB_ERR_ARG, "null pointer");
-  const size_t n = (size_t)Cout * Cin * 9;
+  if (CinPad % 16 || CinPad < Cin) return fail(FB_ERR_SHAPE, "CinPad must be a multiple of 16 and >= Cin");
+  const size_t n = (size_t)Cout * 9 * CinPad / 4;
   wgrad_reduce_kernel<<<ew_grid(n, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(ws, splits, Cout, Cin, CinPad, dw);
   FB_CUDA(cudaGetLastError());
   return FB_OK;

@@ -8,8 +8,18 @@ namespace {
 
 struct WgPlan {
   fb::WgradParams p;
-  int qck, grid, smem, wide, v2;
+  int qck, grid, smem, wide, v2, hp;
 };
+
+// halo-P form (Ca == 64, 16-row tiles): default on, FABRIC_B200_WGRAD_HP=0 is the A/B switch, =16 / =64 restrict it to the
+// 13-band stem / to the 64-channel Q chunks
+static int wgrad_hp_mode() {
+  static const int v = [] {
+    const char* e = getenv("FABRIC_B200_WGRAD_HP");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
 
 int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di);
 
@@ -48,9 +58,14 @@ int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di) {
   // M is padding) and on wide Q (Cb >= 256).  wide = 3 picks per shape.
   const bool v2_ok = d->Cb % 64 == 0 && p.bh == 16;
   pl->v2 = (v2_ok && (d->wide == 2 || (d->wide == 3 && d->Ca >= 128 && d->Cb <= 128))) ? 1 : 0;
+  const int hpm = wgrad_hp_mode();
+  // (measured, 64 pairs: 13->64@256 0.355 -> 0.280 ms, 64->64@256 G2 0.624 -> 0.579, G1 0.316 -> 0.296; 64->64@128 0.089 -> 0.098:
+  //  with few tiles per CTA the doubled epilogue shows, so small maps keep the two-item form unless asked: hpm == 2)
+  pl->hp = (!pl->v2 && d->Ca == 64 && p.bh == 16 && d->wide != 0 && (hpm == 2 || ((hpm == 1 || hpm == pl->qck) && p.tiles_total >= 16384)))
+               ? 1 : 0;
   p.m_tiles = (d->Ca + 127) / 128;
   p.n_chunks = pl->v2 ? d->Cb / 32 : d->Cb / pl->qck;
-  p.row_items = pl->v2 ? 1 : (d->Ca == 64 ? 2 : 3);
+  p.row_items = (pl->v2 || pl->hp) ? 1 : (d->Ca == 64 ? 2 : 3);
   const int items = p.m_tiles * p.n_chunks * p.row_items;
   int splits = d->splits;
   if (splits <= 0) {
@@ -70,7 +85,7 @@ int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di) {
     }
   }
   p.splits = splits;
-  const int stage = pl->v2 ? fb::kWg2Stage : fb::wg_stage_bytes(pl->qck);
+  const int stage = pl->v2 ? fb::kWg2Stage : fb::wg_stage_bytes(pl->qck, pl->hp != 0);
   int stages = (di.smem_optin - 2048) / stage;
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(FB_ERR_SHAPE, "not enough shared memory");
@@ -82,9 +97,9 @@ int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di) {
   return FB_OK;
 }
 
-template <int QCK, bool WIDE>
+template <int QCK, bool WIDE, bool HP = false>
 int launch_wgrad(const WgPlan& pl, const CUtensorMap& tP, const CUtensorMap& tQ, cudaStream_t st) {
-  auto k = fb::wgrad_umma_kernel<QCK, WIDE>;
+  auto k = fb::wgrad_umma_kernel<QCK, WIDE, HP>;
   FB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   k<<<pl.grid, fb::kWgThreads, pl.smem, st>>>(tP, tQ, pl.p);
   FB_CUDA(cudaGetLastError());
@@ -127,7 +142,8 @@ int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream) {
   if (!aligned16(d->p) || !aligned16(d->q) || !aligned16(d->ws)) return fail(FB_ERR_ALIGN, "pointers must be 16-byte aligned");
   const fb::WgradParams& p = pl.p;
   CUtensorMap tP, tQ;
-  rc = make_tmap_act(&tP, d->p, p.Ca, p.W, p.H, p.B, p.G, 64, 8, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  // (halo-P form: one box of 18 rows -- the 16-row tile plus a row above and below)
+  rc = make_tmap_act(&tP, d->p, p.Ca, p.W, p.H, p.B, p.G, 64, 8, pl.hp ? 18 : p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (pl.v2) rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, 32, 10, 18, 1, CU_TENSOR_MAP_SWIZZLE_64B);
   else rc = make_tmap_act(&tQ, d->q, p.Cb, p.W, p.H, p.B, p.G, pl.qck, 10, p.bh, p.bn,
@@ -141,6 +157,7 @@ int fabric_b200_conv3x3_wgrad(const fb_wgrad_desc* d, void* stream) {
     FB_CUDA(cudaGetLastError());
     return FB_OK;
   }
+  if (pl.hp) return pl.qck == 64 ? launch_wgrad<64, true, true>(pl, tP, tQ, st) : launch_wgrad<16, true, true>(pl, tP, tQ, st);
   if (pl.qck == 64) return pl.wide ? launch_wgrad<64, true>(pl, tP, tQ, st) : launch_wgrad<64, false>(pl, tP, tQ, st);
   return pl.wide ? launch_wgrad<16, true>(pl, tP, tQ, st) : launch_wgrad<16, false>(pl, tP, tQ, st);
 }

@@ -35,15 +35,25 @@ struct WgradParams {
 
 constexpr int kWgThreads = 192;
 constexpr int kWgPBytes = 2 * 16384;             // two 64-channel atoms of 128 pixels
+constexpr int kWgPHaloBytes = 18 * 1024;         // HP: ONE 64-channel tile of 18 rows x 8 pixels (the 16 rows + a row above / below)
 // Q stage: 160 pixel slots (16 rows x 10 columns) x QCK channels; QCK = 16 is the 13-band stem (32B swizzle)
 __host__ __device__ constexpr int wg_q_bytes(int QCK) { return 160 * QCK * 2; }
-__host__ __device__ constexpr int wg_stage_bytes(int QCK) { return kWgPBytes + wg_q_bytes(QCK); }
+__host__ __device__ constexpr int wg_stage_bytes(int QCK, bool HP = false) { return (HP ? kWgPHaloBytes : kWgPBytes) + wg_q_bytes(QCK); }
 
-template <int QCK, bool WIDE>
+// HP ("halo P", Ca == 64 on maps of 16 rows or more): ONE work item per (Q chunk, K split) covers all three filter rows.  The P
+// tile is loaded once WITH a row above and below (18 rows x 8 pixels x 64 channels); a filter row is a start-address offset of
+// one tile row (1024 B) into that buffer, and the two M atoms of an MMA are the same buffer one row apart (leading-byte-offset
+// 1024: atom 0 = filter row 1, atom 1 = filter row 0; a second MMA takes filter row 2, its upper half is not stored).  The plain
+// form loads the P tile once per filter row: 3 x 16 KB + 2 Q tiles per pixel tile across its two items -- the 13-band stem
+// (N = 48, almost no math per byte) was bound by exactly that L2 -> shared-memory traffic (ncu: 3.75 GB in 0.38 ms).
+template <int QCK, bool WIDE, bool HP = false>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, const WgradParams p) {
   static_assert(QCK == 64 || QCK == 16, "Q channel chunk");
-  constexpr int kWgStage = wg_stage_bytes(QCK);
+  static_assert(!HP || WIDE, "the halo-P form issues the wide (three filter columns) MMA");
+  constexpr int kWgStage = wg_stage_bytes(QCK, HP);
+  constexpr int kPBytes = HP ? kWgPHaloBytes : kWgPBytes;
+  constexpr int kTmemCols = HP ? (QCK == 64 ? 512 : 128) : 256;
   constexpr uint32_t PIX = QCK * 2;                 // bytes per pixel of the Q tile
   constexpr uint32_t Q_LAYOUT = QCK == 64 ? kLayoutSw128 : kLayoutSw32;
   constexpr int NQ = QCK;                           // N per filter column
@@ -69,7 +79,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
   const int nc = it % p.n_chunks;
   const int mt = it / p.n_chunks;
   // the two P atoms: (channel offset, filter row); row < 0 = empty atom
-  const bool ca64 = p.row_items == 2;
+  const bool ca64 = !HP && p.row_items == 2;
   const int ra = ca64 ? (ri == 0 ? 0 : 2) : ri;
   const int rb = ca64 ? (ri == 0 ? 1 : -1) : ri;
   const int ca_a = mt * 128, ca_b = ca64 ? 0 : mt * 128 + 64;
@@ -81,7 +91,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     prefetch_tmap(&tmQ);
   }
   if (warp == 1) {
-    tmem_alloc(base + bar_off + 512, 256);
+    tmem_alloc(base + bar_off + 512, kTmemCols);
     tmem_relinquish();
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
@@ -112,11 +122,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
       mbar_wait(empty(stage), phase ^ 1);
       if (elect_one()) {
         const uint32_t dst = base + stage * kWgStage;
-        mbar_arrive_expect_tx(full(stage), kWgStage);  // P: 2 x 16 KB, Q: 160 pixel slots
-        tma_load_5d(dst, &tmP, full(stage), ca_a, x0, y0 + 1 - ra, b0, g);
-        // empty atom: a channel coordinate beyond Ca makes the whole box out of bounds = zero filled
-        tma_load_5d(dst + 16384, &tmP, full(stage), rb < 0 ? p.Ca : ca_b, x0, y0 + 1 - (rb < 0 ? 0 : rb), b0, g);
-        tma_load_5d(dst + kWgPBytes, &tmQ, full(stage), nc * QCK, x0 - 1, y0, b0, g);
+        mbar_arrive_expect_tx(full(stage), kWgStage);  // P: 2 x 16 KB (HP: 18 KB), Q: 160 pixel slots
+        if constexpr (HP) {
+          tma_load_5d(dst, &tmP, full(stage), 0, x0, y0 - 1, b0, g);   // rows y0-1 .. y0+16 (out of image = zero filled)
+        } else {
+          tma_load_5d(dst, &tmP, full(stage), ca_a, x0, y0 + 1 - ra, b0, g);
+          // empty atom: a channel coordinate beyond Ca makes the whole box out of bounds = zero filled
+          tma_load_5d(dst + 16384, &tmP, full(stage), rb < 0 ? p.Ca : ca_b, x0, y0 + 1 - (rb < 0 ? 0 : rb), b0, g);
+        }
+        tma_load_5d(dst + kPBytes, &tmQ, full(stage), nc * QCK, x0 - 1, y0, b0, g);
       }
       __syncwarp();
       if (++stage == p.stages) stage = 0, phase ^= 1;
@@ -127,9 +141,10 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     constexpr uint32_t idesc = umma_idesc_bf16(128, WIDE ? 3 * NQ : NQ, 1, 1);
     constexpr uint32_t B_LBO = WIDE ? PIX : 16384;   // WIDE: the next N atom is the same buffer one pixel further
     constexpr uint32_t B_SBO = 10 * PIX;             // 8-pixel K group stride = one halo row
-    constexpr uint64_t a_hi = umma_desc(0, 16384, 1024, kLayoutSw128) & 0xFFFFFFFF00000000ull;
+    constexpr uint32_t A_LBO = HP ? 1024 : 16384;    // HP: the second M atom is the same buffer one tile row further
+    constexpr uint64_t a_hi = umma_desc(0, A_LBO, 1024, kLayoutSw128) & 0xFFFFFFFF00000000ull;
     constexpr uint64_t b_hi = umma_desc(0, B_LBO, B_SBO, Q_LAYOUT) & 0xFFFFFFFF00000000ull;
-    constexpr uint32_t a_lo_fixed = static_cast<uint32_t>(umma_desc(0, 16384, 0, 0) & 0xFFFFFFFFu);
+    constexpr uint32_t a_lo_fixed = static_cast<uint32_t>(umma_desc(0, A_LBO, 0, 0) & 0xFFFFFFFFu);
     constexpr uint32_t b_lo_fixed = static_cast<uint32_t>(umma_desc(0, B_LBO, 0, 0) & 0xFFFFFFFFu);
     constexpr uint32_t B_JSTEP = (2 * B_SBO) >> 4, B_SSTEP = PIX >> 4;
     int stage = 0;
@@ -140,10 +155,14 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_lo = a_lo_fixed + ((base + stage * kWgStage) >> 4);
-        const uint32_t b_lo = b_lo_fixed + ((base + stage * kWgStage + kWgPBytes) >> 4);
+        const uint32_t b_lo = b_lo_fixed + ((base + stage * kWgStage + kPBytes) >> 4);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 16 pixels (two tile rows) per MMA
-          if constexpr (WIDE) {
+          if constexpr (HP) {
+            // P halo row = Q row - r + 2: filter rows (1, 0) start one row down, filter row 2 at the top of the buffer
+            umma_bf16(tmem_base, a_hi | (a_lo + j * 128 + 64), b_hi | (b_lo + j * B_JSTEP), idesc, accumulate);
+            umma_bf16(tmem_base + 3 * NQ, a_hi | (a_lo + j * 128), b_hi | (b_lo + j * B_JSTEP), idesc, accumulate);
+          } else if constexpr (WIDE) {
             umma_bf16(tmem_base, a_hi | (a_lo + j * 128), b_hi | (b_lo + j * B_JSTEP), idesc, accumulate);
           } else {
 #pragma unroll
@@ -163,32 +182,36 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
     // epilogue: 128 rows (P channels) x 3 taps x 64 Q channels -> fp32 partial slab of this split
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    // accumulator row -> (dW row, filter row)
-    const int r = row < 64 ? ra : rb;
-    const int ca = row < 64 ? ca_a + row : ca_b + (row - 64);
     if (t_end > t_begin) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
     }
+    // HP: two accumulator blocks; block 0 rows 0-63 = filter row 1, rows 64-127 = filter row 0; block 1 rows 0-63 = filter row 2
 #pragma unroll 1
-    for (int s = 0; s < 3; ++s) {
+    for (int blk = 0; blk < (HP ? 2 : 1); ++blk) {
+      // accumulator row -> (dW row, filter row)
+      const int r = HP ? (blk == 0 ? (row < 64 ? 1 : 0) : (row < 64 ? 2 : -1)) : (row < 64 ? ra : rb);
+      const int ca = HP ? (row & 63) : (row < 64 ? ca_a + row : ca_b + (row - 64));
 #pragma unroll 1
-      for (int cc = 0; cc < (NQ + 31) / 32; ++cc) {
-        uint32_t v[32];
-        if (t_end > t_begin) {
-          // (for NQ = 16 this reads 16 columns past the tap's accumulator; they are simply not stored)
-          tmem_ld_32x32(tmem_base + s * NQ + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
-          tmem_ld_wait();
-        } else {
+      for (int s = 0; s < 3; ++s) {
+#pragma unroll 1
+        for (int cc = 0; cc < (NQ + 31) / 32; ++cc) {
+          uint32_t v[32];
+          if (t_end > t_begin) {
+            // (for NQ = 16 this reads 16 columns past the tap's accumulator; they are simply not stored)
+            tmem_ld_32x32(tmem_base + blk * 3 * NQ + s * NQ + cc * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (r >= 0 && ca < p.Ca) {
-          float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)split * p.Ca + ca) * 9 + (r * 3 + s)) * p.Cb + nc * QCK + cc * 32);
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          if (r >= 0 && ca < p.Ca) {
+            float4* dst = reinterpret_cast<float4*>(p.ws + (((size_t)split * p.Ca + ca) * 9 + (r * 3 + s)) * p.Cb + nc * QCK + cc * 32);
 #pragma unroll
-          for (int i = 0; i < (NQ < 32 ? NQ : 32) / 4; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
+            for (int i = 0; i < (NQ < 32 ? NQ : 32) / 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+          }
         }
       }
     }
@@ -197,7 +220,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
