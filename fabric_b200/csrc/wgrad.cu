@@ -61,7 +61,8 @@ int plan_wgrad_on(const fb_wgrad_desc* d, WgPlan* pl, const DeviceInfo& di) {
   const int hpm = wgrad_hp_mode();
   // (measured, 64 pairs: 13->64@256 0.355 -> 0.280 ms, 64->64@256 G2 0.624 -> 0.579, G1 0.316 -> 0.296; 64->64@128 0.089 -> 0.098:
   //  with few tiles per CTA the doubled epilogue shows, so small maps keep the two-item form unless asked: hpm == 2)
-  pl->hp = (!pl->v2 && d->Ca == 64 && p.bh == 16 && d->wide != 0 && (hpm == 2 || ((hpm == 1 || hpm == pl->qck) && p.tiles_total >= 16384)))
+  pl->hp = (!pl->v2 && d->Ca == 64 && p.bh == 16 && d->wide != 0 &&
+            (hpm == 2 || d->wide == 4 || ((hpm == 1 || hpm == pl->qck) && p.tiles_total >= 16384)))
                ? 1 : 0;
   p.m_tiles = (d->Ca + 127) / 128;
   p.n_chunks = pl->v2 ? d->Cb / 32 : d->Cb / pl->qck;
