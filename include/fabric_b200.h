@@ -261,7 +261,8 @@ typedef struct {
   int wide;        /* 0 = three N=64 MMAs per K step, 1 = one N=192 MMA (overlapping N atoms), 2 = second form: the filter
                       row goes through an 18-row Q halo tile, 32-channel Q chunks, three N=96 MMAs per K step (falls back
                       to 1 for Cb = 16 and maps of 8 rows or fewer), 3 = 2 where it measured faster (Ca >= 128 and
-                      Cb <= 128), else 1 */
+                      Cb <= 128), else 1; 4 = 1 with the halo-P tile forced (Ca == 64, H > 8: ONE 18-row P tile per pixel
+                      tile serves all three filter rows; modes 1 and 3 choose it by themselves from 16384 pixel tiles up) */
 } fb_wgrad_desc;
 /* the launch plan on a device with `sms` SMs / `smem_optin` bytes of opt-in shared memory (pure host arithmetic) */
 typedef struct {
