@@ -507,6 +507,8 @@ def main():
         # owns the flat gradient bucket (+ fused SGD); FABRIC_B200_NO_OVERLAP=1: one all-reduce after backward (A/B switch)
         dp = DataParallelStep(model, overlap=os.environ.get("FABRIC_B200_NO_OVERLAP", "0") != "1")
         dp.broadcast_parameters(0)
+        if os.environ.get("FABRIC_B200_HIPRI", "1") != "0":       # (A/B switch, tools/ab.sh)
+            dp.use_compute_stream()     # the loop runs on a high-priority stream: main chain ahead of the side-stream wgrads
 
         def step(a=x1, b=x2, lab=labels):                            # train.py:88-95
             dp.zero_grad()

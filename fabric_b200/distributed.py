@@ -103,6 +103,22 @@ class DataParallelStep:
         if manage_packed and dev.type == "cuda":
             self._manage_packed()
 
+    def use_compute_stream(self):
+        """Make a HIGH-PRIORITY stream the current stream of this device (call once, before the training loop).  The backward
+        pass puts the weight-gradient launches on a default-priority side stream (fabric_b200.autograd); with the main chain
+        (data gradient -> BatchNorm backward -> ...) on a high-priority stream its kernels are scheduled first whenever both
+        wait for SMs, and the weight gradients fill in behind them.  Measured: -0.13 .. -0.24 ms per step (three A/B pairs,
+        tools/ab.sh FABRIC_B200_HIPRI).  Returns the stream."""
+        if self.device.type != "cuda":
+            return None
+        if getattr(self, "compute_stream", None) is None:
+            self.compute_stream = torch.cuda.Stream(self.device, priority=-1)
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self.compute_stream:
+            self.compute_stream.wait_stream(cur)
+            torch.cuda.set_stream(self.compute_stream)
+        return self.compute_stream
+
     # ------------------------------------------------------------------------------------------------ basics
     @property
     def world(self):
