@@ -1116,8 +1116,8 @@ __device__ __forceinline__ typename QVec<V>::type bn_act_packed(const typename Q
   }
 }
 
-template <bool GP, bool APPLY, int V, bool EVEN = false>
-__global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz_,
+template <bool GP, bool APPLY, int V, bool EVEN = false, bool PIPE = false>
+__global__ void __launch_bounds__(128, V == 8 ? 2 : (PIPE ? 2 : 4)) bn_bwd2q_kernel(BnBwd p, const float* __restrict__ coef, uint4* __restrict__ dz_,
                                                                      float* __restrict__ partial) {
   using T = typename QVec<V>::type;
   extern __shared__ float sm[];  // reduce: [blockDim][2 * V]
@@ -1146,11 +1146,9 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
       for (int j = 0; j < V; ++j) kb[g][j] = kc[g][j] = 0.f;
     }
   }
-  for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
+  // one quad: its 14 loads ...
+  auto load_quad = [&](uint32_t q, T (&zv)[2][4], T (&gq)[4], T (&gpv)[2], uint32_t (&pix)[4], bool (&ok)[4], bool& pool_ok) {
     const uint32_t qx = q % Wq, t = q / Wq, qy = t % Hq, b = t / Hq;
-    T zv[2][4], gq[4], gpv[2];
-    bool ok[4];
-    uint32_t pix[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       const uint32_t y = 2 * qy + (d >> 1), x = 2 * qx + (d & 1);
@@ -1162,11 +1160,15 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
         gq[d] = __ldg(GA + (size_t)pix[d] * ga_cv + cv);
       }
     }
-    const bool pool_ok = GP && (EVEN || (qy < Hp && qx < Wp));   // (then the whole window exists)
+    pool_ok = GP && (EVEN || (qy < Hp && qx < Wp));   // (then the whole window exists)
     if (pool_ok) {
       gpv[0] = __ldg(GPP + (size_t)((b * Hp + qy) * Wp + qx) * CV + cv);
       gpv[1] = __ldg(GPP + (size_t)(((p.B + b) * Hp + qy) * Wp + qx) * CV + cv);
     }
+  };
+  // ... and its arithmetic
+  auto do_quad = [&](const T (&zv)[2][4], const T (&gq)[4], const T (&gpv)[2], const uint32_t (&pix)[4], const bool (&ok)[4],
+                     const bool pool_ok) {
     // activations of both dates as the forward pass stored them (bf16), kept packed
     T av[2][4];
 #pragma unroll
@@ -1222,6 +1224,32 @@ __global__ void __launch_bounds__(128, V == 8 ? 2 : 4) bn_bwd2q_kernel(BnBwd p, 
           }
         }
       }
+    }
+  };
+  if constexpr (PIPE) {
+    // software pipeline over two register sets: the loads of quad i+1 are in flight while quad i is computed (the plain loop
+    // issued them only after the arithmetic of quad i: every warp alternated between waiting and computing)
+    T zvA[2][4], gqA[4], gpA[2], zvB[2][4], gqB[4], gpB[2];
+    uint32_t pixA[4], pixB[4];
+    bool okA[4], okB[4], poA = false, poB = false;
+    uint32_t q = blockIdx.x * ppb + lane_p;
+    if (q < nquad) load_quad(q, zvA, gqA, gpA, pixA, okA, poA);
+    while (q < nquad) {
+      if (q + stride < nquad) load_quad(q + stride, zvB, gqB, gpB, pixB, okB, poB);
+      do_quad(zvA, gqA, gpA, pixA, okA, poA);
+      q += stride;
+      if (q >= nquad) break;
+      if (q + stride < nquad) load_quad(q + stride, zvA, gqA, gpA, pixA, okA, poA);
+      do_quad(zvB, gqB, gpB, pixB, okB, poB);
+      q += stride;
+    }
+  } else {
+    for (uint32_t q = blockIdx.x * ppb + lane_p; q < nquad; q += stride) {
+      T zv[2][4], gq[4], gpv[2];
+      bool ok[4], pool_ok;
+      uint32_t pix[4];
+      load_quad(q, zv, gq, gpv, pix, ok, pool_ok);
+      do_quad(zv, gq, gpv, pix, ok, pool_ok);
     }
   }
   if (!APPLY) {
@@ -1532,11 +1560,14 @@ int64_t fabric_b200_outconv_bwd_ws_floats(int C) {
 
 // reduce-pass blocks per SM at most (the partial array is [blocks][G][C][2])
 constexpr int kBnBwdMaxBlk = 4;
-// channels per thread of the quad kernels: 4 (default) or 8 (FABRIC_B200_BWD2Q_V=8: the A/B switch)
+// quad kernels, A/B switch FABRIC_B200_BWD2Q_V: default (7) = 4 channels per thread, even-size specialisation, loads of the next
+// quad software-pipelined under the arithmetic of the current one (two register sets, 2 blocks per SM: measured 2.16 -> 2.01 ms
+// for the eight launches of a step against 4 = the same without the pipeline at 4 blocks per SM); 5 = 4 with generic quads;
+// 8 = the first form (8 channels per thread, 2.50 ms); 8 also switches the plain-case kernels back to the generic ones
 static int bwd2q_vec() {
   static const int v = [] {
     const char* e = getenv("FABRIC_B200_BWD2Q_V");
-    return (e && e[0] == '8') ? 8 : (e && e[0] == '5') ? 5 : 4;
+    return (e && e[0] == '8') ? 8 : (e && e[0] == '5') ? 5 : (e && e[0] == '4') ? 4 : 7;
   }();
   return v;
 }
@@ -1580,17 +1611,19 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
   const bool quad = dual && !a;
   const int qv = (quad && bwd2q_vec() != 8 && C / 4 <= 128 && 128 % (C / 4) == 0) ? 4 : 8;
   const bool even = H % 2 == 0 && W % 2 == 0 && bwd2q_vec() != 5;   // (FABRIC_B200_BWD2Q_V=5: 4 channels, generic quads)
+  const bool pipe = bwd2q_vec() == 7;                                // (=7: software-pipelined loads, 2 blocks per SM)
   // = resident blocks: one balanced wave (256 threads x 2 per SM; the quad kernels 128 threads x 2 or 4 per SM)
   // plain case (one gradient source, no product / pool): the specialised kernels, 3 blocks of 256 threads per SM
   const bool plain = ga && !gp && !mul_other && bwd2q_vec() != 8;
   const uint32_t npix_ = (uint32_t)B * H * W;
-  const int nblk = di.sms * ((quad && qv == 4) ? 4 : plain ? 3 : 2);
+  const int nblk = di.sms * ((quad && qv == 4) ? (bwd2q_vec() == 7 ? 2 : 4) : plain ? 3 : 2);
   float* partial = ws;
   float* coef = ws + (size_t)nblk * G * C * 2;
   if (phase & 1) {
     const size_t sm2 = 256 * 16 * sizeof(float), sm1 = 128 * 2 * qv * sizeof(float);
     // (the recompute variants run nblk blocks of 128 threads: the partial layout [nblk][G][C][2] is the same)
-    if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, false, 4, true><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    if (quad && gp && qv == 4 && even && pipe) bn_bwd2q_kernel<true, false, 4, true, true><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
+    else if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, false, 4, true><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (quad && gp && qv == 4) bn_bwd2q_kernel<true, false, 4><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (quad && gp) bn_bwd2q_kernel<true, false, 8><<<nblk, 128, sm1, st>>>(p, nullptr, nullptr, partial);
     else if (dual && gp) bn_bwd2_reduce_kernel<true, false><<<nblk, 256, sm2, st>>>(p, partial);
@@ -1610,7 +1643,8 @@ static int bn_relu_bwd_phases(int phase, const void* z, const void* a, const voi
     uint4* dzo = reinterpret_cast<uint4*>(dz);
     const size_t nq = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / qv);   // quad-threads per date
     const int g1 = ew_grid(nq, 128, di.sms);
-    if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, true, 4, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    if (quad && gp && qv == 4 && even && pipe) bn_bwd2q_kernel<true, true, 4, true, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
+    else if (quad && gp && qv == 4 && even) bn_bwd2q_kernel<true, true, 4, true><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (quad && gp && qv == 4) bn_bwd2q_kernel<true, true, 4><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (quad && gp) bn_bwd2q_kernel<true, true, 8><<<g1, 128, 0, st>>>(p, coef, dzo, nullptr);
     else if (dual && gp) bn_bwd2_apply_kernel<true, false><<<g2, 256, 0, st>>>(p, coef, dzo);
