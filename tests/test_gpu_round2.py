@@ -826,7 +826,7 @@ def test_training_step_with_and_without_stored_encoder_activations_agree(cuda):
             assert rel(res[0][1][k], res[1][1][k]) <= 1e-2 or float(res[1][1][k].abs().max()) == 0.0, k
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (2, 45, 45), (1, 7, 5)])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 32), (2, 45, 45), (1, 7, 5), (6, 256, 256)])   # (the last: unrolled main loops)
 def test_fused_bn_head_forward_and_backward_match_the_separate_kernels(cuda, B, H, W):
     """bn_apply_relu_head == bn_apply_relu + outconv (activation bit-equal, logits to fp32 summation order); bn_head_bwd ==
     outconv_bwd + bn_relu_bwd up to the bf16 rounding of the du tensor the fused path never materialises; incl. pixel

@@ -115,7 +115,9 @@ def test_bn_train_forward_matches_torch(cuda):
     (2, 2, 32, 32, 13, 64, 2), (2, 5, 4, 4, 128, 128, 2),
     # halo-P form (64 dL/dz channels, maps of 16 rows or more: all three filter rows from ONE 18-row P tile), ragged edges
     # (wide = 4 forces it on these small maps; the planner's default needs >= 16384 pixel tiles)
-    (1, 2, 45, 45, 64, 64, 4), (2, 2, 40, 27, 13, 64, 4), (1, 3, 17, 9, 64, 64, 4), (2, 1, 64, 64, 64, 64, 4), (1, 2, 32, 24, 64, 64, 4)])
+    (1, 2, 45, 45, 64, 64, 4), (2, 2, 40, 27, 13, 64, 4), (1, 3, 17, 9, 64, 64, 4), (2, 1, 64, 64, 64, 64, 4), (1, 2, 32, 24, 64, 64, 4),
+    # 16384 pixel tiles: what the planner picks by itself at the benchmark batch (halo-P for both; many tiles per K split)
+    (2, 16, 256, 256, 13, 64, 3), (2, 16, 256, 256, 64, 64, 3)])
 def test_wgrad_matches_torch(cuda, G, B, H, W, cin, cout, wide):
     from fabric_b200 import ops
     torch.manual_seed(3)
@@ -177,10 +179,10 @@ def test_up_input_bwd_is_adjoint_of_bilinear_pad(cuda, H, W, h, w):
     assert rel(dlow[0].float(), low.grad.permute(0, 2, 3, 1)) <= 5e-3
 
 
-def _bn_bwd_case(cuda, quad, pool=True):
+def _bn_bwd_case(cuda, quad, pool=True, shape=(2, 2, 13, 10, 64), recompute=False):
     from fabric_b200 import ops
     torch.manual_seed(6)
-    G, B, H, W, C = 2, 2, 13, 10, 64
+    G, B, H, W, C = shape
     z = torch.randn(G, B, H, W, C, device=cuda).bfloat16()
     gam = torch.empty(C, device=cuda).uniform_(0.5, 1.5).requires_grad_(True)
     bet = (0.3 * torch.randn(C, device=cuda)).requires_grad_(True)
@@ -205,7 +207,8 @@ def _bn_bwd_case(cuda, quad, pool=True):
         for g in range(G if pool else 0):
             loss = loss + (gp[g].float().permute(0, 3, 1, 2) * F.max_pool2d(acts[g], 2)).sum()
         loss.backward()
-        dz, dg, db = ops.bn_relu_bwd(z, a5, gcat, True, gp, scale, shift, mean.contiguous(), invstd.contiguous(), gam)
+        dz, dg, db = ops.bn_relu_bwd(z, None if recompute else a5, gcat, True, gp, scale, shift, mean.contiguous(),
+                                     invstd.contiguous(), gam)
     else:
         ga = torch.randn(G, B, H, W, C, device=cuda).bfloat16()
         sum((ga[g].float() * a_ref[g]).sum() for g in range(G)).backward()
@@ -221,6 +224,19 @@ def test_bn_relu_bwd_plain(cuda):
 def test_bn_relu_bwd_with_product_and_pool_adjoints(cuda):
     e = _bn_bwd_case(cuda, True)      # the other date's activation enters as a bf16 tensor: looser
     assert e[0] <= 1.5e-2 and e[1] <= 5e-3 and e[2] <= 5e-3
+
+
+@pytest.mark.parametrize("quad,shape", [(False, (2, 6, 256, 256, 64)), (False, (1, 3, 200, 168, 128)), (True, (2, 4, 128, 128, 64)),
+                                        (True, (2, 3, 64, 96, 128)), (True, (2, 3, 45, 45, 128))])
+def test_bn_relu_bwd_large_maps_run_the_unrolled_main_loops(cuda, quad, shape):
+    """The same two cases at sizes where a thread walks several pixels / quads: the plain-case kernels' four-pixels-in-flight
+    main loop plus tail, and the quad kernel's software pipeline (even sizes; the odd 45 x 45 case takes the generic quads),
+    with the activation recomputed from z as the training step does."""
+    e = _bn_bwd_case(cuda, quad, shape=shape, recompute=quad)
+    if quad:   # (dz: the fp32 reference multiplies by the un-rounded activation of the other date; measured 1.2e-2 .. 1.5e-2)
+        assert e[0] <= 2e-2 and e[1] <= 5e-3 and e[2] <= 5e-3, e
+    else:
+        assert e[0] <= 5e-3 and e[1] <= 1e-4 and e[2] <= 1e-4, e
 
 
 def test_bn_relu_bwd_with_product_only(cuda):
