@@ -498,9 +498,13 @@ __global__ void reduce_partials_kernel(const float* __restrict__ ws, int n, int 
     // eight independent fp64 chains (fixed order: deterministic): one chain of ~300 dependent loads took 47 us
     double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int i = 0;
+    const float* col = ws + j;
     for (; i + 8 <= n; i += 8) {
+      float v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += ws[(size_t)(i + k) * m + j];
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(col + (size_t)(i + k) * m);   // all eight loads first
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += (double)v[k];
     }
     for (; i < n; ++i) s[0] += ws[(size_t)i * m + j];
     out[j] = (float)(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
