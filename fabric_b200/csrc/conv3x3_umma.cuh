@@ -145,6 +145,15 @@ struct IntC {
 struct TileCoord {
   int n0, x0, y0, b0, g;
 };
+// epilogue options (one bit each; see the kernel's `flags`)
+enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128,
+                  F_INIT = 256, F_BNB = 512 };
+// FIX instantiations: the option set is a template argument (ReLU on, no affine: BatchNorm folded, shift primed in TMEM), so
+// every option test folds at compile time.  The generic eval epilogue spends ~150 of its ~490 warp instructions per
+// 32-column chunk on those tests (ncu source view of inc.c2: BRA 46, ISETP 49, PLOP3 16, LDCU 16, BSYNC 10 per chunk) and is
+// what bounds the 64-wide layers (tensor pipe 52 %, issue slots 40 %: `profiles/r02_ncu_source.md`).
+constexpr uint32_t kFixLean = F_PROD | F_POOL | F_POOL_TMA | F_PROD_TMA | F_TWO | F_INIT;   // encoder c2: pooled copy + date product
+
 // n / d for n * d < 2^40 as one 64-bit multiply: m = ceil(2^40 / d) (host).  Replaces MUFU.RCP division sequences in
 // the per-tile paths of all three warp roles.
 __device__ __forceinline__ int fast_div(int n, unsigned long long m) {
@@ -191,7 +200,7 @@ __device__ __forceinline__ bool tile_at(const Conv3x3Params& p, int it, int N_TI
 // Its epilogue is raw-accumulator store (+ BatchNorm moments, or + the fused BatchNorm-backward reduce) only -- pooling,
 // product fusion, the 1x1 head, the affine / ReLU and accumulator-priming paths are compiled out -- and the per-channel sums
 // accumulate in registers across the CTA's tiles (see REGSTATS below).
-template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1, bool RS = false>
+template <int N_TILE, int CK, bool HALO, bool RES, int CTAS, int EW, int MINB = 1, bool RS = false, uint32_t FIX = 0>
 __global__ void __launch_bounds__(conv_threads(EW), MINB)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP,
@@ -541,9 +550,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int pn = (m >> 3) / p.bh;
     // this warp's 4 tile rows (32 pixels) as a TMA store box: rows [wy, wy + min(bh,4)) of images [wn, ...)
     const int wn = (q * 4) / p.bh, wy = (q * 4) % p.bh;
-    const bool affine = !RS && !p.acc_init && (p.scale != nullptr || p.shift != nullptr);
-    const bool relu = !RS && p.relu != 0;
-    const bool extras = p.stats_out || p.pool_out || p.prod_out || p.head_out;   // one branch for the common plain tile
+    static_assert(FIX == 0 || !RS, "a fixed option set is an eval-mode instantiation");
+    const bool affine = FIX ? false : (!RS && !p.acc_init && (p.scale != nullptr || p.shift != nullptr));
+    const bool relu = FIX ? true : (!RS && p.relu != 0);
+    const bool extras = FIX ? (FIX & (F_STATS | F_POOL | F_PROD | F_HEAD)) != 0u
+                            : (p.stats_out || p.pool_out || p.prod_out || p.head_out);   // one branch for the common plain tile
     // moments in registers: with at most two 32-column chunks per warp the per-tile transposing shuffle tree (62 shuffles and
     // ~250 selects / adds per chunk: measured +0.14 .. +0.28 ms on the 64- and 128-wide training convolutions) is replaced by
     // plain per-thread accumulation over the CTA's tiles; the tree runs once per date group
@@ -591,19 +602,19 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
     // epilogue options as ONE opaque register: the chunk loop tests bits instead of re-reading kernel parameters through
     // the constant bank (LDCU + ISETP + BRA per test, each a latency bubble with one or two warps per scheduler)
-    enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 16, F_PROD_TMA = 32, F_HEAD = 64, F_TWO = 128,
-                      F_INIT = 256, F_BNB = 512 };
     uint32_t flags = (p.store_main ? F_MAIN : 0u) | (p.prod_out ? F_PROD : 0u) | ((p.stats_out && !p.bnb_z) ? F_STATS : 0u) |
                      (p.bnb_z ? F_BNB : 0u) |
                      (p.pool_out ? F_POOL : 0u) | (p.pool_tma ? F_POOL_TMA : 0u) | (p.prod_tma ? F_PROD_TMA : 0u) |
                      (p.head_out ? F_HEAD : 0u) | (p.out_bufs == 2 ? F_TWO : 0u) | (p.acc_init ? F_INIT : 0u);
     if constexpr (RS) flags &= (F_MAIN | F_STATS | F_BNB);   // the only epilogue options of the training instantiation
-    asm volatile("mov.b32 %0, %0;" : "+r"(flags));
+    if constexpr (FIX != 0u) flags = FIX;                    // (the host launches this instantiation for exactly this set)
+    else asm volatile("mov.b32 %0, %0;" : "+r"(flags));
     // flag test; in the RS instantiation every other option folds to false at compile time (its code and registers vanish)
     // (per-channel sums of narrow tiles live in the RS instantiation only; the 13-band stem has no data gradient)
     constexpr uint32_t kAllowed = (RS ? (F_MAIN | F_STATS | F_BNB) : (CPW <= 2 ? ~(F_STATS | F_BNB) : ~0u)) &
                                   (CK == 16 ? ~static_cast<uint32_t>(F_BNB) : ~0u);
     auto has = [&](const uint32_t f) -> bool {
+      if constexpr (FIX != 0u) return (FIX & f) != 0u;
       if ((f & kAllowed) == 0u) return false;
       return (flags & f & kAllowed) != 0u;
     };
