@@ -636,6 +636,7 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
                         (p.bnb_z ? fb::F_BNB : 0u) | (p.pool_out ? fb::F_POOL : 0u) | (p.pool_tma ? fb::F_POOL_TMA : 0u) |
                         (p.prod_tma ? fb::F_PROD_TMA : 0u) | (p.head_out ? fb::F_HEAD : 0u) | (p.out_bufs == 2 ? fb::F_TWO : 0u) |
                         (p.acc_init ? fb::F_INIT : 0u);
+    // (the training instantiation's three option sets fixed the same way measured no gain: its epilogue already folds)
     if (fix_on && !pl.rs && p.relu && p.acc_init && pl.n_tile == 64 && pl.ck == 64 && pl.halo && res && pl.ctas == 2 && pl.ew == 8) {
       // measured (eval forward, 64 pairs): inc.c2 0.662 -> 0.570 ms, down1.c2 likewise.  (A fixed {main output} set for the 64-wide
       // decoder convs measured 2-3 % SLOWER than the generic epilogue -- 92 registers, other schedule --, the same set on the

@@ -550,10 +550,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int pn = (m >> 3) / p.bh;
     // this warp's 4 tile rows (32 pixels) as a TMA store box: rows [wy, wy + min(bh,4)) of images [wn, ...)
     const int wn = (q * 4) / p.bh, wy = (q * 4) % p.bh;
-    static_assert(FIX == 0 || !RS, "a fixed option set is an eval-mode instantiation");
     const bool affine = FIX ? false : (!RS && !p.acc_init && (p.scale != nullptr || p.shift != nullptr));
-    const bool relu = FIX ? true : (!RS && p.relu != 0);
-    const bool extras = FIX ? (FIX & (F_STATS | F_POOL | F_PROD | F_HEAD)) != 0u
+    const bool relu = RS ? false : (FIX ? true : (p.relu != 0));
+    const bool extras = FIX ? (FIX & (F_STATS | F_BNB | F_POOL | F_PROD | F_HEAD)) != 0u
                             : (p.stats_out || p.pool_out || p.prod_out || p.head_out);   // one branch for the common plain tile
     // moments in registers: with at most two 32-column chunks per warp the per-tile transposing shuffle tree (62 shuffles and
     // ~250 selects / adds per chunk: measured +0.14 .. +0.28 ms on the 64- and 128-wide training convolutions) is replaced by
