@@ -118,7 +118,7 @@ int fabric_b200_conv3x3_wgrad_plan(const fb_wgrad_desc* d, int sms, int smem_opt
   WgPlan pl;
   int rc = plan_wgrad_on(d, &pl, di);
   if (rc) return rc;
-  out->form = pl.v2 ? 2 : 1, out->grid = pl.grid, out->splits = pl.p.splits, out->stages = pl.p.stages;
+  out->form = pl.v2 ? 2 : (pl.hp ? 3 : 1), out->grid = pl.grid, out->splits = pl.p.splits, out->stages = pl.p.stages;
   out->smem_bytes = pl.smem, out->items = pl.grid / pl.p.splits, out->tiles_total = pl.p.tiles_total;
   return FB_OK;
 }

@@ -266,7 +266,8 @@ typedef struct {
 } fb_wgrad_desc;
 /* the launch plan on a device with `sms` SMs / `smem_optin` bytes of opt-in shared memory (pure host arithmetic) */
 typedef struct {
-  int form;        /* 1 = filter row through the P tile, 2 = through the Q halo tile */
+  int form;        /* 1 = filter row through the P tile, 2 = through the Q halo tile, 3 = form 1 with ONE 18-row P halo tile for
+                      all three filter rows (Ca == 64) */
   int grid, items, splits, stages, smem_bytes, tiles_total;
 } fb_wgrad_plan;
 int fabric_b200_conv3x3_wgrad_plan(const fb_wgrad_desc* d, int sms, int smem_optin, fb_wgrad_plan* out);

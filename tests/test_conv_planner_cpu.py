@@ -138,7 +138,11 @@ def test_wgrad_grid_fills_whole_waves(lib, name, G, H, cin, cout):
     rc, p = wgrad_plan(lib, G, 64, H, H, cout, cin)          # P = dL/dz has the layer's OUTPUT channels
     assert rc == 0, lib.fabric_b200_last_error()
     assert p.smem_bytes <= SMEM and p.stages >= 2
-    assert p.form == (2 if (cout >= 128 and 64 <= cin <= 128) else 1)
+    # second form where it measured faster; halo-P form for 64 dL/dz channels from 16384 pixel tiles up (the 256 x 256 layers)
+    want = 2 if (cout >= 128 and 64 <= cin <= 128) else (3 if (cout == 64 and p.tiles_total >= 16384) else 1)
+    assert p.form == want, (p.form, want, p.tiles_total)
+    if p.form == 3:
+        assert p.items == max(1, (16 if cin <= 16 else cin) // 64)      # ONE item per Q chunk covers all three filter rows
     assert p.grid == p.items * p.splits and p.splits * 4 <= p.tiles_total
     waves = -(-p.grid // SMS)
     assert p.grid / (waves * SMS) >= 0.85, (p.grid, waves)    # every wave at least 85 % full
@@ -150,6 +154,12 @@ def test_wgrad_grid_fills_whole_waves(lib, name, G, H, cin, cout):
 def test_wgrad_forms_and_fallbacks(lib):
     assert wgrad_plan(lib, 2, 64, 128, 128, 128, 128, wide=1)[1].form == 1
     assert wgrad_plan(lib, 2, 64, 128, 128, 128, 128, wide=2)[1].form == 2
-    assert wgrad_plan(lib, 2, 64, 256, 256, 64, 13, wide=2)[1].form == 1      # 13-band stem: first form only
+    assert wgrad_plan(lib, 2, 64, 256, 256, 64, 13, wide=2)[1].form == 3      # 13-band stem: never the second form (first form, halo-P at this size)
     assert wgrad_plan(lib, 2, 5, 4, 4, 128, 128, wide=2)[1].form == 1         # maps of 8 rows or fewer
     assert wgrad_plan(lib, 1, 1, 16, 16, 96, 64)[0] != 0                      # Ca must be a multiple of 64
+    # halo-P: forced by wide = 4 on small maps, never for Ca != 64 or maps of 8 rows or fewer, not with the three-MMA form
+    assert wgrad_plan(lib, 1, 2, 32, 24, 64, 64, wide=4)[1].form == 3 and wgrad_plan(lib, 1, 2, 32, 24, 64, 64, wide=1)[1].form == 1
+    assert wgrad_plan(lib, 1, 2, 32, 24, 128, 64, wide=4)[1].form == 1 and wgrad_plan(lib, 1, 8, 8, 8, 64, 64, wide=4)[1].form == 1
+    assert wgrad_plan(lib, 2, 64, 256, 256, 64, 13, wide=0)[1].form == 1
+    # the operand-swapped call of ops.conv3x3_wgrad for up4.c1 (p = the 128-channel input, q = 64-channel dL/dz): second form
+    assert wgrad_plan(lib, 1, 64, 256, 256, 128, 64)[1].form == 2
