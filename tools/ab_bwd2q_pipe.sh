@@ -1,7 +1,7 @@
 #!/bin/bash
 O=gpurun_out; mkdir -p $O
 F="--steps 1 --warmup 3 --no-cpu-baseline --no-library --no-scene --no-infer --no-small --e2e-steps 1"
-for v in 7; do
+for v in 4 7; do
   FABRIC_B200_BWD2Q_V=$v timeout 600 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:bn_bwd2q --csv --log-file $O/r02v_bwd2q_v$v.csv python bench.py $F > /dev/null 2>&1
   python - $O/r02v_bwd2q_v$v.csv <<'PY'
 import csv,sys
