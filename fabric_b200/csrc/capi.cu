@@ -637,11 +637,20 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
                         (p.prod_tma ? fb::F_PROD_TMA : 0u) | (p.head_out ? fb::F_HEAD : 0u) | (p.out_bufs == 2 ? fb::F_TWO : 0u) |
                         (p.acc_init ? fb::F_INIT : 0u);
     // (the training instantiation's three option sets fixed the same way measured no gain: its epilogue already folds)
+    static const bool fix_more = [] {       // (=1: only the lean set -- the A/B switch of the head and stem sets)
+      const char* e = getenv("FABRIC_B200_CONV_FIX");
+      return !(e && e[0] == '1');
+    }();
+    if (fix_on && fix_more && !pl.rs && p.relu && p.acc_init && pl.n_tile == 64 && pl.ck == 16 && pl.halo && res && pl.ctas == 2 &&
+        pl.ew == 4 && pl.minb == 2 && fl == fb::kFixMain)
+      return launch_conv<64, 16, true, true, 2, 4, 2, false, fb::kFixMain>(pl, tA, tB, tY, tP, tQ, st);
     if (fix_on && !pl.rs && p.relu && p.acc_init && pl.n_tile == 64 && pl.ck == 64 && pl.halo && res && pl.ctas == 2 && pl.ew == 8) {
-      // measured (eval forward, 64 pairs): inc.c2 0.662 -> 0.570 ms, down1.c2 likewise.  (A fixed {main output} set for the 64-wide
+      // measured (eval forward, 64 pairs): inc.c2 0.662 -> 0.570 ms, down1.c2 likewise; up4.c2 + head 0.314 -> 0.275 ms; the 13-band
+      // stem (four epilogue warps, two CTAs per SM) 0.382 -> 0.303 ms.  (A fixed {main output} set for the 64-wide
       // decoder convs measured 2-3 % SLOWER than the generic epilogue -- 92 registers, other schedule --, the same set on the
       // 256-wide product tiles (down2.c2) no different: neither is instantiated.)
       if (fl == fb::kFixLean) return launch_conv<64, 64, true, true, 2, 8, 1, false, fb::kFixLean>(pl, tA, tB, tY, tP, tQ, st);
+      if (fl == fb::kFixHead && fix_more) return launch_conv<64, 64, true, true, 2, 8, 1, false, fb::kFixHead>(pl, tA, tB, tY, tP, tQ, st);
     }
   }
 #define FB_LAUNCH(NT, CK, HL, RS, EW)                                                                   \

@@ -153,6 +153,8 @@ enum : uint32_t { F_MAIN = 1, F_PROD = 2, F_STATS = 4, F_POOL = 8, F_POOL_TMA = 
 // 32-column chunk on those tests (ncu source view of inc.c2: BRA 46, ISETP 49, PLOP3 16, LDCU 16, BSYNC 10 per chunk) and is
 // what bounds the 64-wide layers (tensor pipe 52 %, issue slots 40 %: `profiles/r02_ncu_source.md`).
 constexpr uint32_t kFixLean = F_PROD | F_POOL | F_POOL_TMA | F_PROD_TMA | F_TWO | F_INIT;   // encoder c2: pooled copy + date product
+constexpr uint32_t kFixHead = F_HEAD | F_INIT;                                              // up4.c2: only the 1x1 head's logits leave
+constexpr uint32_t kFixMain = F_MAIN | F_INIT;                                              // the 13-band stem: main output only
 
 // n / d for n * d < 2^40 as one 64-bit multiply: m = ceil(2^40 / d) (host).  Replaces MUFU.RCP division sequences in
 // the per-tile paths of all three warp roles.
