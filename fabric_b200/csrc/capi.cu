@@ -636,7 +636,8 @@ int fabric_b200_conv3x3(const fb_conv3x3_desc* d, void* stream) {
                         (p.bnb_z ? fb::F_BNB : 0u) | (p.pool_out ? fb::F_POOL : 0u) | (p.pool_tma ? fb::F_POOL_TMA : 0u) |
                         (p.prod_tma ? fb::F_PROD_TMA : 0u) | (p.head_out ? fb::F_HEAD : 0u) | (p.out_bufs == 2 ? fb::F_TWO : 0u) |
                         (p.acc_init ? fb::F_INIT : 0u);
-    // (the training instantiation's three option sets fixed the same way measured no gain: its epilogue already folds)
+    // (the training instantiation's option sets fixed the same way -- 64-wide layers and the stem -- measured no gain: its
+    //  epilogue already folds)
     static const bool fix_more = [] {       // (=1: only the lean set -- the A/B switch of the head and stem sets)
       const char* e = getenv("FABRIC_B200_CONV_FIX");
       return !(e && e[0] == '1');
